@@ -1,0 +1,225 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY -- see oracle/petiga_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product package petiga_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6)
+FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(native=False):
+    """Compile the oracle with gcc (a few seconds).  native=True adds -march=native (CPU-baseline timing)."""
+    name = "libpetiga_oracle_native.so" if native else "libpetiga_oracle.so"
+    out = os.path.join(_HERE, name)
+    src = os.path.join(_HERE, "petiga_oracle.c")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    march = "native" if native else "x86-64-v2"
+    cmd = ["gcc", "-O2", "-march=" + march, "-fPIC", "-shared", "-o", out, src, "-lm"]
+    subprocess.check_call(cmd, cwd=_HERE)
+    return out
+
+
+def lib(native=False):
+    global _LIB
+    if _LIB is not None and not native:
+        return _LIB
+    path = os.path.join(_HERE, "libpetiga_oracle_native.so" if native else "libpetiga_oracle.so")
+    if native or not os.path.exists(path):
+        try:
+            path = build(native)
+        except Exception:
+            if native:
+                return lib(False)
+            raise
+    L = C.CDLL(path)
+    L.oiga_create.restype = C.c_void_p
+    L.oiga_create.argtypes = [C.c_int, C.c_int]
+    L.oiga_destroy.argtypes = [C.c_void_p]
+    L.oiga_axis_init_uniform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.oiga_axis_set_knots.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
+    L.oiga_set_rule_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.oiga_set_order.argtypes = [C.c_void_p, C.c_int]
+    L.oiga_set_boundary_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.oiga_set_boundary_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.oiga_set_geometry.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.oiga_set_fixtable.argtypes = [C.c_void_p, _dp, C.c_long]
+    L.oiga_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.oiga_get_info.argtypes = [C.c_void_p, _ip]
+    for name, rt in [("oiga_knots", _dp), ("oiga_spans", _ip), ("oiga_basis_offset", _ip), ("oiga_basis_detJac", _dp),
+                     ("oiga_basis_weight", _dp), ("oiga_basis_point", _dp), ("oiga_basis_value", _dp)]:
+        getattr(L, name).restype = rt
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+    L.oiga_lgmap.restype = _ip
+    L.oiga_lgmap.argtypes = [C.c_void_p]
+    L.oiga_partition.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
+    L.oiga_pattern_create.restype = C.c_void_p
+    L.oiga_pattern_create.argtypes = [C.c_void_p, C.c_int]
+    L.oiga_pattern_destroy.argtypes = [C.c_void_p]
+    L.oiga_pattern_nrows.argtypes = [C.c_void_p]
+    L.oiga_pattern_nnz.restype = C.c_long
+    L.oiga_pattern_nnz.argtypes = [C.c_void_p]
+    for name in ("oiga_pattern_rowptr", "oiga_pattern_colidx", "oiga_pattern_rank_rowstart"):
+        getattr(L, name).restype = _ip
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.oiga_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
+                                C.c_void_p, _dp, _dp]
+    L.oiga_tabulate_element.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 12
+    if not native:
+        _LIB = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class OracleIGA:
+    """Mirror of the reference's IGA object restricted to what the assembly path reads."""
+
+    def __init__(self, dim, dof=1, native=False):
+        self.L = lib(native)
+        self.dim, self.dof = dim, dof
+        self.h = self.L.oiga_create(dim, dof)
+        self._pat = {}
+
+    def __del__(self):
+        try:
+            for p in self._pat.values():
+                self.L.oiga_pattern_destroy(p)
+            self.L.oiga_destroy(self.h)
+        except Exception:
+            pass
+
+    # -- discretisation ---------------------------------------------------------------------
+    def axis_uniform(self, axis, p, N, Ui=0.0, Uf=1.0, C=-1, periodic=False):
+        assert self.L.oiga_axis_init_uniform(self.h, axis, p, N, Ui, Uf, C, int(periodic)) == 0
+
+    def axis_knots(self, axis, p, U, periodic=False):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert self.L.oiga_axis_set_knots(self.h, axis, p, len(U) - 1, _d(U), int(periodic)) == 0
+
+    def rule_size(self, axis, q):
+        self.L.oiga_set_rule_size(self.h, axis, q)
+
+    def order(self, k):
+        self.L.oiga_set_order(self.h, k)
+
+    def boundary_value(self, axis, side, field, value):
+        self.L.oiga_set_boundary_value(self.h, axis, side, field, value)
+
+    def boundary_load(self, axis, side, field, value):
+        self.L.oiga_set_boundary_load(self.h, axis, side, field, value)
+
+    def geometry(self, X, W=None):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        nsd = X.shape[-1]
+        Wc = None if W is None else np.ascontiguousarray(W, dtype=np.float64)
+        self.L.oiga_set_geometry(self.h, nsd, _d(X), _d(Wc))
+
+    def fixtable(self, U):
+        if U is None:
+            self.L.oiga_set_fixtable(self.h, None, 0)
+        else:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+            self.L.oiga_set_fixtable(self.h, _d(U), U.size)
+
+    def setup(self, size=1, rank=0):
+        rc = self.L.oiga_setup(self.h, size, rank)
+        assert rc == 0, rc
+        return self.info()
+
+    def info(self):
+        buf = (C.c_int * 46)()
+        self.L.oiga_get_info(self.h, buf)
+        keys = ["p", "m", "nnp", "nel", "nqp", "nen", "proc_size", "proc_rank", "elem_start", "elem_width",
+                "node_lstart", "node_lwidth", "node_gstart", "node_gwidth", "geom_size"]
+        out = {"order": buf[0]}
+        for k, key in enumerate(keys):
+            out[key] = [buf[1 + 15 * i + k] for i in range(3)]
+        return out
+
+    def tables(self, axis):
+        inf = self.info()
+        nel, nqp, nen, m = inf["nel"][axis], inf["nqp"][axis], inf["nen"][axis], inf["m"][axis]
+        g = lambda f, n, dt: np.ctypeslib.as_array(f(self.h, axis), shape=(n,)).astype(dt, copy=True)
+        return dict(
+            U=g(self.L.oiga_knots, m + 1, np.float64), span=g(self.L.oiga_spans, nel, np.int32),
+            offset=g(self.L.oiga_basis_offset, nel, np.int32), detJac=g(self.L.oiga_basis_detJac, nel, np.float64),
+            weight=g(self.L.oiga_basis_weight, nel * nqp, np.float64).reshape(nel, nqp),
+            point=g(self.L.oiga_basis_point, nel * nqp, np.float64).reshape(nel, nqp),
+            value=g(self.L.oiga_basis_value, nel * nqp * nen * 5, np.float64).reshape(nel, nqp, nen, 5))
+
+    def lgmap(self):
+        inf = self.info()
+        n = int(np.prod(inf["node_gwidth"]))
+        return np.ctypeslib.as_array(self.L.oiga_lgmap(self.h), shape=(n,)).copy()
+
+    # -- pattern + assembly -----------------------------------------------------------------
+    def pattern(self, size=1):
+        """Global block-CSR pattern in PETSc numbering: (rowptr, colidx, rank_rowstart)."""
+        if size not in self._pat:
+            p = self.L.oiga_pattern_create(self.h, size)
+            assert p
+            self._pat[size] = p
+        p = self._pat[size]
+        n, nnz = self.L.oiga_pattern_nrows(p), self.L.oiga_pattern_nnz(p)
+        rp = np.ctypeslib.as_array(self.L.oiga_pattern_rowptr(p), shape=(n + 1,)).copy()
+        ci = np.ctypeslib.as_array(self.L.oiga_pattern_colidx(p), shape=(nnz,)).copy()
+        rs = np.ctypeslib.as_array(self.L.oiga_pattern_rank_rowstart(p), shape=(size + 1,)).copy()
+        return rp, ci, rs
+
+    def assemble(self, slot, form, params=(), size=1, shift=0.0, V=None, t=0.0, U=None):
+        """Returns (values[nnzb, dof, dof] or None, rhs[nrows, dof] or None) of one full assembly."""
+        rp, ci, _ = self.pattern(size)
+        p = self._pat[size]
+        n, nnz, dof = len(rp) - 1, len(ci), self.dof
+        slot_i = SLOT[slot]
+        want_mat = slot in ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN")
+        want_vec = slot in ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION")
+        vals = np.zeros((nnz, dof, dof)) if want_mat else None
+        rhs = np.zeros((n, dof)) if want_vec else None
+        prm = np.ascontiguousarray(list(params) + [0.0] * 4, dtype=np.float64)
+        Uc = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
+        Vc = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+        rc = self.L.oiga_assemble(self.h, size, slot_i, FORM[form], _d(prm), shift, _d(Vc), t, _d(Uc), p, _d(vals), _d(rhs))
+        assert rc == 0, "oracle assemble failed rc=%d" % rc
+        return vals, rhs
+
+    def tabulate(self, ID, order=3):
+        inf = self.info()
+        nqp, nen = int(np.prod(inf["nqp"])), int(np.prod(inf["nen"]))
+        dim = self.dim
+        nsd = dim
+        o = dict(weight=np.zeros(nqp), detJac=np.zeros(nqp), detX=np.zeros(nqp), point=np.zeros((nqp, dim)),
+                 X0=np.zeros((nqp, nsd)), X1=np.zeros((nqp, nsd, dim)), X2=np.zeros((nqp, nsd, dim, dim)),
+                 X3=np.zeros((nqp, nsd, dim, dim, dim)), shape0=np.zeros((nqp, nen)), shape1=np.zeros((nqp, nen, nsd)),
+                 shape2=np.zeros((nqp, nen, nsd, nsd)), shape3=np.zeros((nqp, nen, nsd, nsd, nsd)))
+        ID3 = (C.c_int * 3)(*(list(ID) + [0, 0, 0])[:3])
+        q, a = C.c_int(), C.c_int()
+        self.L.oiga_tabulate_element(self.h, ID3, C.byref(q), C.byref(a), *[_d(o[k]) for k in
+                                     ("weight", "detJac", "detX", "point", "X0", "X1", "X2", "X3",
+                                      "shape0", "shape1", "shape2", "shape3")])
+        return o
+
+
+def partition(size, rank, dim, N):
+    L = lib()
+    Na = (C.c_int * 3)(*(list(N) + [1, 1, 1])[:3])
+    n = (C.c_int * 3)(0, 0, 0)
+    i = (C.c_int * 3)(0, 0, 0)
+    rc = L.oiga_partition(size, rank, dim, Na, n, i)
+    assert rc == 0, rc
+    return list(n)[:dim], list(i)[:dim]

@@ -1,0 +1,78 @@
+"""Geometry fixtures shared by the oracle and GPU tests (pure numpy; no reference code)."""
+import numpy as np
+
+
+def greville(U, p):
+    U = np.asarray(U)
+    n = len(U) - p - 1
+    return np.array([U[i + 1:i + p + 1].sum() / p for i in range(n)])
+
+
+def uniform_knots(p, N, C=None, lo=0.0, hi=1.0):
+    C = p - 1 if C is None else C
+    s = p - C
+    inner = np.repeat(lo + np.arange(1, N) / N * (hi - lo), s)
+    return np.concatenate([[lo] * (p + 1), inner, [hi] * (p + 1)])
+
+
+def perturbed_identity(dim, p, N, amp=0.05):
+    """SURVEY 8d cfg 2g: control points = Greville abscissae + amp*prod sin(2 pi x_d) per component, W = 1.
+    Returns X[natural (k,j,i)][dim]."""
+    N = [N] * dim if np.isscalar(N) else N
+    g = [greville(uniform_knots(p, N[d]), p) for d in range(dim)]
+    grids = np.meshgrid(*g[::-1], indexing="ij")[::-1]   # grids[d] indexed [k][j][i]
+    bump = amp * np.prod([np.sin(2 * np.pi * x) for x in grids], axis=0)
+    return np.stack([grids[d] + bump for d in range(dim)], axis=-1)
+
+
+def _insert_knot_1d(U, p, Pw, u):
+    """Boehm knot insertion on homogeneous control points Pw[n, c] (textbook A5.1 for one knot)."""
+    k = np.searchsorted(U, u, side="right") - 1
+    n = len(Pw)
+    Q = np.zeros((n + 1, Pw.shape[1]))
+    Q[:k - p + 1] = Pw[:k - p + 1]
+    Q[k + 1:] = Pw[k:]
+    for i in range(k - p + 1, k + 1):
+        a = (u - U[i]) / (U[i + p] - U[i])
+        Q[i] = a * Pw[i] + (1 - a) * Pw[i - 1]
+    return np.insert(U, k + 1, u), Q
+
+
+def refine_annulus(cls, N=(4, 4), p=2, dof=1, height=None):
+    """Quarter annulus of test/IGAGeometryMap.c:18-32 knot-refined to N elements per axis (exact NURBS).
+    Returns (iga object of class `cls` with axes+geometry set, X, W).  dim = 2, or 3 when height is given."""
+    s2 = np.sqrt(2.0)
+    PX = np.array([[1.0, 1.0, 0.0], [1.5, 1.5, 0.0], [2.0, 2.0, 0.0]])
+    PY = np.array([[0.0, 1.0, 1.0], [0.0, 1.5, 1.5], [0.0, 2.0, 2.0]])
+    PW = np.array([[1.0, s2 / 2, 1.0]] * 3)
+    # homogeneous net [i (radial)][j (angular)][x*w, y*w, w]
+    net = np.stack([PX * PW, PY * PW, PW], axis=-1)
+    U0 = np.array([0, 0, 0, 1, 1, 1.0])
+    U1 = U0.copy()
+    for u in np.arange(1, N[0]) / N[0]:
+        U0, flat = _insert_knot_1d(U0, 2, net.reshape(net.shape[0], -1), u)
+        net = flat.reshape(-1, net.shape[1], 3)
+    for v in np.arange(1, N[1]) / N[1]:
+        t = net.transpose(1, 0, 2)
+        U1, flat = _insert_knot_1d(U1, 2, t.reshape(t.shape[0], -1), v)
+        net = flat.reshape(-1, t.shape[1], 3).transpose(1, 0, 2)
+    W = net[..., 2]
+    XY = net[..., :2] / W[..., None]
+    dim = 2 if height is None else 3
+    o = cls(dim, dof)
+    o.axis_knots(0, 2, U0)
+    o.axis_knots(1, 2, U1)
+    if dim == 2:
+        X = XY.transpose(1, 0, 2).copy()          # natural order [j][i][c]
+        Wn = W.T.copy()
+    else:
+        Nz, hz = height
+        U2 = uniform_knots(2, Nz)
+        o.axis_knots(2, 2, U2)
+        gz = greville(U2, 2) * hz
+        X = np.zeros((len(gz),) + XY.transpose(1, 0, 2).shape[:2] + (3,))
+        X[..., :2] = XY.transpose(1, 0, 2)[None]
+        X[..., 2] = gz[:, None, None]
+        Wn = np.broadcast_to(W.T[None], X.shape[:3]).copy()
+    o.geometry(X, Wn)
+    return o, X, Wn
