@@ -1,0 +1,157 @@
+/*
+ * petiga_host.h -- PETSc-free host mirror of the slice of PetIGA's public API (include/petiga.h of the
+ * reference) that surrounds the element-assembly path, implemented on top of the C ABI in petiga_cuda.h.
+ *
+ * Why it exists: the reference is a PETSc library and this image has no PETSc/MPI, so the reference's own
+ * drivers cannot be linked here.  This mirror keeps the reference's names, argument meaning and error
+ * behaviour (PetscErrorCode returns, "must call X first" state checks) so that the parity tests read like
+ * the reference's demos (demo/Poisson3D.c:26-67 etc.).  With PETSc present, the same calls are made from
+ * PetIGA's re-written driver bodies instead.
+ *
+ * Differences forced by the missing dependencies (each is marked below):
+ *   - MPI_Comm  -> IGAComm {rank, size, nccl communicator, device}
+ *   - Mat / Vec -> minimal device-resident CSR / array objects with the AIJ / BAIJ value layouts
+ *   - form callbacks are host function pointers in the reference; the GPU cannot call them, so the
+ *     IGASetForm* setters accept only the exported IGADeviceForm_* sentinels (same signatures as
+ *     include/petiga.h:153-171) and fail with PETSC_ERR_SUP for any other pointer.
+ */
+#ifndef PETIGA_HOST_H
+#define PETIGA_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int PetscErrorCode;
+typedef int PetscInt;
+typedef double PetscReal;
+typedef double PetscScalar;
+typedef int PetscBool;
+#define PETSC_TRUE 1
+#define PETSC_FALSE 0
+#define PETSC_DECIDE (-1)
+
+/* PETSc error codes used by the mirrored functions (petscerror.h values) */
+#define PETSC_ERR_MEM 55
+#define PETSC_ERR_SUP 56
+#define PETSC_ERR_ORDER 58
+#define PETSC_ERR_ARG_OUTOFRANGE 63
+#define PETSC_ERR_ARG_WRONG 62
+#define PETSC_ERR_ARG_WRONGSTATE 73
+#define PETSC_ERR_LIB 76
+#define PETSC_ERR_USER 83
+#define PETSC_ERR_ARG_NULL 85
+
+typedef struct { int rank, size; void *nccl; int device; } IGAComm;   /* stands in for MPI_Comm */
+
+typedef struct _p_IGA *IGA;
+typedef struct _n_IGAAxis *IGAAxis;
+typedef struct _n_IGAPoint *IGAPoint;       /* opaque here: forms run on the device */
+typedef struct _p_Mat *Mat;
+typedef struct _p_Vec *Vec;
+
+/* callback signatures of include/petiga.h:153-171 */
+typedef PetscErrorCode (*IGAFormVector)(IGAPoint p, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormMatrix)(IGAPoint p, PetscScalar *K, void *ctx);
+typedef PetscErrorCode (*IGAFormSystem)(IGAPoint p, PetscScalar *K, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormFunction)(IGAPoint p, const PetscScalar *U, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormJacobian)(IGAPoint p, const PetscScalar *U, PetscScalar *J, void *ctx);
+typedef PetscErrorCode (*IGAFormIFunction)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormIJacobian)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *J, void *ctx);
+
+/* ---- device-form sentinels: pass these where the reference passes the demo's callback; ctx points at the
+        demo's AppCtx (its leading PetscReal members are the parameters).  Calling them on the host fails. ---- */
+PetscErrorCode IGADeviceForm_Poisson_System(IGAPoint, PetscScalar *, PetscScalar *, void *);            /* demo/Poisson{1,2,3}D.c System      */
+PetscErrorCode IGADeviceForm_Poisson_Function(IGAPoint, const PetscScalar *, PetscScalar *, void *);    /* residual of the same problem        */
+PetscErrorCode IGADeviceForm_Poisson_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_Laplace_System(IGAPoint, PetscScalar *, PetscScalar *, void *);            /* demo/Laplace.c SystemGalerkin       */
+PetscErrorCode IGADeviceForm_L2Projection_System(IGAPoint, PetscScalar *, PetscScalar *, void *);       /* ctx: {PetscReal choice}             */
+PetscErrorCode IGADeviceForm_Mass_System(IGAPoint, PetscScalar *, PetscScalar *, void *);               /* test/IGACreate.c System             */
+PetscErrorCode IGADeviceForm_Mass_Matrix(IGAPoint, PetscScalar *, void *);                              /* test/IGACreate.c Matrix             */
+PetscErrorCode IGADeviceForm_Mass_Vector(IGAPoint, PetscScalar *, void *);                              /* test/IGACreate.c Vector             */
+PetscErrorCode IGADeviceForm_Elasticity3D_System(IGAPoint, PetscScalar *, PetscScalar *, void *);       /* ctx: {lambda, mu}                   */
+PetscErrorCode IGADeviceForm_Elasticity_System(IGAPoint, PetscScalar *, PetscScalar *, void *);         /* ctx: {mu, lambda} as demo/Elasticity.c:10-13 */
+PetscErrorCode IGADeviceForm_CahnHilliard2D_Residual(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *); /* ctx: {theta, alpha} */
+PetscErrorCode IGADeviceForm_CahnHilliard2D_Tangent(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_Bratu_Function(IGAPoint, const PetscScalar *, PetscScalar *, void *);      /* ctx: {lambda}                       */
+PetscErrorCode IGADeviceForm_Bratu_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_Bratu_IFunction(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_Bratu_IJacobian(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+
+/* ---- IGA object: include/petiga.h:393-460 ---- */
+PetscErrorCode IGACreate(IGAComm comm, IGA *iga);
+PetscErrorCode IGADestroy(IGA *iga);
+PetscErrorCode IGASetDim(IGA iga, PetscInt dim);
+PetscErrorCode IGAGetDim(IGA iga, PetscInt *dim);
+PetscErrorCode IGASetDof(IGA iga, PetscInt dof);
+PetscErrorCode IGAGetDof(IGA iga, PetscInt *dof);
+PetscErrorCode IGASetOrder(IGA iga, PetscInt order);
+PetscErrorCode IGASetProcessors(IGA iga, PetscInt i, PetscInt processors);
+PetscErrorCode IGAGetAxis(IGA iga, PetscInt i, IGAAxis *axis);
+PetscErrorCode IGASetRuleSize(IGA iga, PetscInt i, PetscInt nqp);
+PetscErrorCode IGASetMatType(IGA iga, const char *mattype);            /* "aij" or "baij" (petiga.c:1326-1330 default) */
+PetscErrorCode IGASetUp(IGA iga);
+/* geometry in natural ordering, i fastest, (n_d+1) control points per axis: X[..][nsd], W[..] or NULL.
+   Stands in for IGALoadGeometry (src/petigaio.c:201-286), which reads the same arrays from a PETSc binary file. */
+PetscErrorCode IGASetGeometryArrays(IGA iga, PetscInt nsd, const PetscReal *X, const PetscReal *W);
+
+/* ---- axis: include/petiga.h:62-89 ---- */
+PetscErrorCode IGAAxisSetPeriodic(IGAAxis axis, PetscBool periodic);
+PetscErrorCode IGAAxisSetDegree(IGAAxis axis, PetscInt p);
+PetscErrorCode IGAAxisSetKnots(IGAAxis axis, PetscInt m, const PetscReal U[]);
+PetscErrorCode IGAAxisInitUniform(IGAAxis axis, PetscInt N, PetscReal Ui, PetscReal Uf, PetscInt C);
+PetscErrorCode IGAAxisGetSizes(IGAAxis axis, PetscInt *nel, PetscInt *nnp);
+
+/* ---- boundary conditions and forms: include/petiga.h:297-308 ---- */
+PetscErrorCode IGASetBoundaryValue(IGA iga, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value);
+PetscErrorCode IGASetBoundaryLoad(IGA iga, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value);
+PetscErrorCode IGASetFixTable(IGA iga, Vec table);
+PetscErrorCode IGASetFormVector(IGA iga, IGAFormVector Vector, void *ctx);
+PetscErrorCode IGASetFormMatrix(IGA iga, IGAFormMatrix Matrix, void *ctx);
+PetscErrorCode IGASetFormSystem(IGA iga, IGAFormSystem System, void *ctx);
+PetscErrorCode IGASetFormFunction(IGA iga, IGAFormFunction Function, void *ctx);
+PetscErrorCode IGASetFormJacobian(IGA iga, IGAFormJacobian Jacobian, void *ctx);
+PetscErrorCode IGASetFormIFunction(IGA iga, IGAFormIFunction IFunction, void *ctx);
+PetscErrorCode IGASetFormIJacobian(IGA iga, IGAFormIJacobian IJacobian, void *ctx);
+
+/* ---- Mat / Vec: src/petigamat.c:345-549, src/petigavec.c:78-113 ---- */
+PetscErrorCode IGACreateMat(IGA iga, Mat *mat);
+PetscErrorCode IGACreateVec(IGA iga, Vec *vec);
+PetscErrorCode MatDestroy(Mat *mat);
+PetscErrorCode VecDestroy(Vec *vec);
+/* sizes: local rows (scalar), local nnz in the matrix's own layout (scalars for AIJ, blocks for BAIJ), block size */
+PetscErrorCode MatGetSizesIGA(Mat mat, PetscInt *nrows, int64_t *nnz, PetscInt *bs, PetscBool *baij);
+PetscErrorCode MatGetCSRHost(Mat mat, PetscInt *rowptr, PetscInt *colidx, PetscScalar *values);   /* any may be NULL */
+PetscErrorCode MatGetValuesDevice(Mat mat, PetscScalar **d_values);
+PetscErrorCode VecGetLocalSize(Vec vec, PetscInt *n);
+PetscErrorCode VecGetArrayHost(Vec vec, PetscScalar *out);
+PetscErrorCode VecSetArrayHost(Vec vec, const PetscScalar *in);
+PetscErrorCode VecGetArrayDevice(Vec vec, PetscScalar **d_array);
+
+/* ---- the seven drivers: include/petiga.h:837-851 ---- */
+PetscErrorCode IGAComputeVector(IGA iga, Vec B);
+PetscErrorCode IGAComputeMatrix(IGA iga, Mat A);
+PetscErrorCode IGAComputeSystem(IGA iga, Mat A, Vec B);
+PetscErrorCode IGAComputeFunction(IGA iga, Vec U, Vec F);
+PetscErrorCode IGAComputeJacobian(IGA iga, Vec U, Mat J);
+PetscErrorCode IGAComputeIFunction(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Vec F);
+PetscErrorCode IGAComputeIJacobian(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Mat J);
+
+/* ---- introspection used by the tests / bench ---- */
+PetscErrorCode IGAGetInfoArray(IGA iga, PetscInt info[46]);     /* same layout as the oracle's oiga_get_info */
+PetscErrorCode IGAGetBasisTable(IGA iga, PetscInt axis, PetscInt which, PetscReal *out);  /* 0 value,1 weight,2 point,3 detJac,4 knots */
+PetscErrorCode IGAGetLGMapHost(IGA iga, PetscInt *lgmap);
+PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* forwarded to petiga_cuda_set_option */
+PetscErrorCode IGAGetStat(IGA iga, const char *name, PetscReal *value);
+PetscErrorCode IGAGetPlan(IGA iga, void **plan);                             /* the petiga_cuda_plan behind the IGA */
+const char *IGAGetLastErrorMessage(void);
+/* pure host logic (no GPU needed): partition of src/petigapart.c */
+PetscErrorCode IGA_Partition(PetscInt size, PetscInt rank, PetscInt dim, const PetscInt N[], PetscInt n[], PetscInt i[]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETIGA_HOST_H */

@@ -1,0 +1,500 @@
+// pc_api.cu -- extern "C" entry points of libpetiga_cuda (see include/petiga_cuda.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "pc_plan.h"
+
+namespace pc {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return PETIGA_CUDA_ERR_NODEVICE;
+  if (e == cudaErrorMemoryAllocation) return PETIGA_CUDA_ERR_MEM;
+  return PETIGA_CUDA_ERR_CUDA;
+}
+
+template <typename T>
+static int upload(petiga_cuda_plan* P, const T* src, size_t n, T** dst) {
+  *dst = nullptr;
+  if (n == 0) n = 1;
+  void* d = nullptr;
+  PC_CUDA(cudaMalloc(&d, n * sizeof(T)));
+  P->allocs.push_back(d);
+  if (src) PC_CUDA(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, P->stream));
+  *dst = static_cast<T*>(d);
+  return 0;
+}
+
+// ---- pattern kernel: one warp per owned row, closed-form positions (IGACreateMat: petigamat.c:448-537) ----
+struct PatParams {
+  const int* rowG[3]; const int* W[3]; const uint32_t* seg[3]; const int* first[3]; const int* own[3];
+  const int* box_ls[3]; const int* box_lw[3]; const int* rank_start; const int64_t* rowbase;
+  int gs[3], nnp[3], Pn[3];
+  int nown, bs;
+  int* colidx;
+};
+
+__global__ void pattern_kernel(const __grid_constant__ PatParams pp) {
+  const int warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + threadIdx.x / 32; row < pp.nown; row += gridDim.x * warps_per_block) {
+    int node[3], g[3], W[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { node[d] = pp.rowG[d][row]; g[d] = node[d] - pp.gs[d]; W[d] = pp.W[d][g[d]]; }
+    const int nw = W[0] * W[1] * W[2];
+    const int64_t base = pp.rowbase[row];
+    for (int e = lane; e < nw; e += 32) {
+      int c[3] = {e % W[0], (e / W[0]) % W[1], e / (W[0] * W[1])};
+      int B[3], S[3], Lc[3], gid_r[3], w[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        uint32_t s = pp.seg[d][g[d] * kMaxW + c[d]];
+        B[d] = s & 255; S[d] = (s >> 8) & 255; Lc[d] = (s >> 16) & 255;
+        int cc = pp.first[d][node[d]] + c[d];
+        w[d] = cc < 0 ? pp.nnp[d] + cc : (cc >= pp.nnp[d] ? cc % pp.nnp[d] : cc);
+        gid_r[d] = pp.own[d][w[d]];
+      }
+      int pos = B[2] * W[1] * W[0] + S[2] * (B[1] * W[0] + S[1] * B[0]) + (Lc[2] * S[1] + Lc[1]) * S[0] + Lc[0];
+      int q = gid_r[0] + pp.Pn[0] * (gid_r[1] + pp.Pn[1] * gid_r[2]);
+      int l0 = pp.box_lw[0][gid_r[0]], l1 = pp.box_lw[1][gid_r[1]];
+      int gid = pp.rank_start[q] + (w[0] - pp.box_ls[0][gid_r[0]]) + l0 * ((w[1] - pp.box_ls[1][gid_r[1]]) + l1 * (w[2] - pp.box_ls[2][gid_r[2]]));
+      if (pp.bs == 1) pp.colidx[base + pos] = gid;
+      else
+        for (int r = 0; r < pp.bs; r++)
+          for (int cc = 0; cc < pp.bs; cc++)
+            pp.colidx[base * pp.bs * pp.bs + (int64_t)r * nw * pp.bs + (int64_t)pos * pp.bs + cc] = gid * pp.bs + cc;
+    }
+  }
+}
+
+__global__ void gather_owned_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" {
+
+int petiga_cuda_version(void) { return PETIGA_CUDA_VERSION; }
+
+const char* petiga_cuda_strerror(int code) {
+  switch (code) {
+    case PETIGA_CUDA_OK: return "success";
+    case PETIGA_CUDA_ERR_ARG: return "invalid argument";
+    case PETIGA_CUDA_ERR_ORDER: return "operation called out of order";
+    case PETIGA_CUDA_ERR_SUP: return "configuration not supported by the device path";
+    case PETIGA_CUDA_ERR_MEM: return "out of memory";
+    case PETIGA_CUDA_ERR_CUDA: return "CUDA runtime error";
+    case PETIGA_CUDA_ERR_NODEVICE: return "no CUDA device (libpetiga_cuda has no CPU fallback)";
+    case PETIGA_CUDA_ERR_NCCL: return "NCCL error";
+  }
+  return "unknown error";
+}
+
+const char* petiga_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int petiga_cuda_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (count) *count = (e == cudaSuccess) ? n : 0;
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  return n > 0 ? 0 : PETIGA_CUDA_ERR_NODEVICE;
+}
+
+int petiga_cuda_plan_create(petiga_cuda_plan** plan, const petiga_cuda_space* sp, int rank, int nranks, void* nccl_comm,
+                            void* stream, int device) {
+  if (!plan || !sp) return PETIGA_CUDA_ERR_ARG;
+  *plan = nullptr;
+  int ndev = 0;
+  int rc = petiga_cuda_device_count(&ndev);
+  if (rc) { if (g_last_error.empty()) set_error("no CUDA device; libpetiga_cuda has no CPU fallback"); return rc; }
+  if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return PETIGA_CUDA_ERR_ARG; }
+  petiga_cuda_plan* P = new (std::nothrow) petiga_cuda_plan();
+  if (!P) return PETIGA_CUDA_ERR_MEM;
+  memset(&P->bc, 0, sizeof(P->bc));
+  rc = build_layout(*sp, rank, nranks, P->L);
+  if (rc) { set_error(P->L.error); delete P; return rc; }
+  if (sp->order < 1 || sp->order > 4) { set_error("order must be in [1,4]"); delete P; return PETIGA_CUDA_ERR_ARG; }
+  P->order = sp->order;
+  P->device = device;
+  P->nccl = nccl_comm;
+  auto bail = [&](int code) { petiga_cuda_plan_destroy(P); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaSetDevice"));
+  if (stream) P->stream = (cudaStream_t)stream;
+  else {
+    cudaError_t e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    P->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&P->num_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaEventCreate(&P->ev0);
+  cudaEventCreate(&P->ev1);
+  const Layout& L = P->L;
+  for (int d = 0; d < 3; d++) {
+    const AxisLayout& a = L.ax[d];
+    DevAxis& da = P->dax[d];
+    const size_t nq = (size_t)a.nel * a.nqp;
+    if (!sp->value[d] || !sp->weight[d] || !sp->point[d] || !sp->detJac[d]) { set_error("missing basis tables"); return bail(PETIGA_CUDA_ERR_ARG); }
+    double *v, *w, *pt, *dj; int *off, *W, *lo; uint32_t* seg;
+    if ((rc = upload(P, sp->value[d], nq * (a.p + 1) * 5, &v))) return bail(rc);
+    if ((rc = upload(P, sp->weight[d], nq, &w))) return bail(rc);
+    if ((rc = upload(P, sp->point[d], nq, &pt))) return bail(rc);
+    if ((rc = upload(P, sp->detJac[d], (size_t)a.nel, &dj))) return bail(rc);
+    if ((rc = upload(P, sp->offset[d], (size_t)a.nel, &off))) return bail(rc);
+    if ((rc = upload(P, a.W.data(), a.W.size(), &W))) return bail(rc);
+    if ((rc = upload(P, a.lo.data(), a.lo.size(), &lo))) return bail(rc);
+    if ((rc = upload(P, a.seg.data(), a.seg.size(), &seg))) return bail(rc);
+    da.value = v; da.weight = w; da.point = pt; da.detJac = dj; da.offset = off; da.W = W; da.lo = lo; da.seg = seg;
+    da.nel = a.nel; da.nqp = a.nqp; da.nen = a.p + 1; da.p = a.p; da.gs = a.gs; da.gw = a.gw; da.es = a.es; da.ew = a.ew;
+    da.periodic = a.periodic; da.nnp = a.nnp;
+    P->detJac_h[d].assign(sp->detJac[d], sp->detJac[d] + a.nel);
+    if ((rc = upload(P, L.rowG[d].data(), L.rowG[d].size(), &P->d_rowG[d]))) return bail(rc);
+    if ((rc = upload(P, a.first.data(), a.first.size(), &P->d_first[d]))) return bail(rc);
+    if ((rc = upload(P, a.own.data(), a.own.size(), &P->d_own[d]))) return bail(rc);
+    if ((rc = upload(P, a.box_ls.data(), a.box_ls.size(), &P->d_box_ls[d]))) return bail(rc);
+    if ((rc = upload(P, a.box_lw.data(), a.box_lw.size(), &P->d_box_lw[d]))) return bail(rc);
+  }
+  if ((rc = upload(P, L.localrow.data(), L.localrow.size(), &P->d_localrow))) return bail(rc);
+  if ((rc = upload(P, L.rowbase.data(), L.rowbase.size(), &P->d_rowbase))) return bail(rc);
+  if ((rc = upload(P, L.rank_start.data(), L.rank_start.size(), &P->d_rank_start))) return bail(rc);
+  if (L.nranks > 1) {
+    const size_t nl = (size_t)L.nloc * L.dof;
+    if ((rc = upload<double>(P, nullptr, nl, &P->d_rhs_loc))) return bail(rc);
+    if ((rc = upload<double>(P, nullptr, nl, &P->d_U_loc))) return bail(rc);
+    if ((rc = upload<double>(P, nullptr, nl, &P->d_V_loc))) return bail(rc);
+    std::vector<int> rows;
+    P->recv_row_off.clear();
+    for (auto& r : L.recv) { P->recv_row_off.push_back(rows.size()); rows.insert(rows.end(), r.rows.begin(), r.rows.end()); }
+    P->recv_row_off.push_back(rows.size());
+    if ((rc = upload(P, rows.data(), rows.size(), &P->d_recv_rows))) return bail(rc);
+  }
+  cudaError_t e = cudaStreamSynchronize(P->stream);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "plan upload"));
+  *plan = P;
+  return 0;
+}
+
+int petiga_cuda_plan_destroy(petiga_cuda_plan* P) {
+  if (!P) return 0;
+  cudaSetDevice(P->device);
+  if (P->stream) cudaStreamSynchronize(P->stream);
+  for (void* d : P->allocs) cudaFree(d);
+  for (int b = 0; b < 2; b++) { cudaFree(P->d_rowptr[b]); cudaFree(P->d_colidx[b]); }
+  cudaFree(P->d_X); cudaFree(P->d_W); cudaFree(P->d_fixtable); cudaFree(P->d_ghost_values); cudaFree(P->d_recv);
+  cudaFree(P->d_values_own); cudaFree(P->d_rhs_own); cudaFree(P->d_U_own); cudaFree(P->d_V_own);
+  if (P->h_pinned) cudaFreeHost(P->h_pinned);
+  if (P->ev0) cudaEventDestroy(P->ev0);
+  if (P->ev1) cudaEventDestroy(P->ev1);
+  if (P->own_stream && P->stream) cudaStreamDestroy(P->stream);
+  delete P;
+  return 0;
+}
+
+int petiga_cuda_set_option(petiga_cuda_plan* P, const char* name, double value) {
+  if (!P || !name) return PETIGA_CUDA_ERR_ARG;
+  if (!strcmp(name, "path")) { int v = (int)value; if (v < 0 || v > 2) return PETIGA_CUDA_ERR_ARG; P->path = v; return 0; }
+  if (!strcmp(name, "scatter")) { P->scatter = (int)value; return 0; }
+  set_error(std::string("unknown option ") + name);
+  return PETIGA_CUDA_ERR_ARG;
+}
+
+int petiga_cuda_get_stat(petiga_cuda_plan* P, const char* name, double* value) {
+  if (!P || !name || !value) return PETIGA_CUDA_ERR_ARG;
+  if (!strcmp(name, "launches")) { *value = (double)P->launches; return 0; }
+  if (!strcmp(name, "last_path")) { *value = (double)P->last_path; return 0; }
+  if (!strcmp(name, "last_kernel_ms")) { *value = P->last_kernel_ms; return 0; }
+  if (!strcmp(name, "num_sms")) { *value = P->num_sms; return 0; }
+  if (!strcmp(name, "nghostrows")) { *value = P->L.nghostrows; return 0; }
+  if (!strcmp(name, "nnz_loc")) { *value = (double)P->L.nnz_loc; return 0; }
+  return PETIGA_CUDA_ERR_ARG;
+}
+
+int petiga_cuda_set_geometry(petiga_cuda_plan* P, int nsd, const double* X, const double* W) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  PC_CUDA(cudaSetDevice(P->device));
+  PC_CUDA(cudaStreamSynchronize(P->stream));
+  cudaFree(P->d_X); cudaFree(P->d_W);
+  P->d_X = P->d_W = nullptr;
+  if (!X) return 0;
+  if (nsd != P->L.dim) { set_error("geometry: nsd must equal dim on the device path (manifolds unsupported)"); return PETIGA_CUDA_ERR_SUP; }
+  const size_t ng = P->L.localrow.size();
+  PC_CUDA(cudaMalloc(&P->d_X, ng * nsd * sizeof(double)));
+  PC_CUDA(cudaMemcpy(P->d_X, X, ng * nsd * sizeof(double), cudaMemcpyHostToDevice));
+  if (W) {
+    PC_CUDA(cudaMalloc(&P->d_W, ng * sizeof(double)));
+    PC_CUDA(cudaMemcpy(P->d_W, W, ng * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int petiga_cuda_set_bc(petiga_cuda_plan* P, const petiga_cuda_bc* bc) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  PC_CUDA(cudaSetDevice(P->device));
+  PC_CUDA(cudaStreamSynchronize(P->stream));
+  cudaFree(P->d_fixtable);
+  P->d_fixtable = nullptr;
+  P->has_bc = false;
+  memset(&P->bc, 0, sizeof(P->bc));
+  if (!bc) return 0;
+  for (int d = 0; d < 3; d++)
+    for (int s = 0; s < 2; s++) {
+      if (bc->vcount[d][s] < 0 || bc->vcount[d][s] > 64 || bc->lcount[d][s] < 0 || bc->lcount[d][s] > 64) return PETIGA_CUDA_ERR_ARG;
+      if (d < P->L.dim && (bc->vcount[d][s] || bc->lcount[d][s])) P->has_bc = true;
+    }
+  P->bc = *bc;
+  P->bc.fixtableU = nullptr;
+  if (bc->fixtableU) {
+    const size_t n = P->L.localrow.size() * P->L.dof;
+    PC_CUDA(cudaMalloc(&P->d_fixtable, n * sizeof(double)));
+    PC_CUDA(cudaMemcpy(P->d_fixtable, bc->fixtableU, n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int petiga_cuda_form_select(petiga_cuda_plan* P, int slot, int form_id, const double* params, int nparams) {
+  if (!P || slot < 0 || slot >= PETIGA_NSLOTS || form_id < 0 || form_id >= PETIGA_NFORMS || nparams < 0 || nparams > 8) {
+    set_error("form_select: bad slot / form / nparams");
+    return PETIGA_CUDA_ERR_ARG;
+  }
+  FormInfo fi = form_info(form_id, slot, P->L.dim, P->L.dof);
+  if (!fi.valid) { set_error("form_select: this built-in form does not provide that slot for this dim/dof (PETSC_ERR_SUP)"); return PETIGA_CUDA_ERR_SUP; }
+  P->slots[slot].form = form_id;
+  memset(P->slots[slot].prm, 0, sizeof(P->slots[slot].prm));
+  for (int k = 0; k < nparams; k++) P->slots[slot].prm[k] = params[k];
+  return 0;
+}
+
+int petiga_cuda_plan_sizes(petiga_cuda_plan* P, int* nown, int* nghost, int64_t* nnzb) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  if (nown) *nown = P->L.nown;
+  if (nghost) *nghost = (int)P->L.localrow.size();
+  if (nnzb) *nnzb = P->L.nnz_own;
+  return 0;
+}
+
+int petiga_cuda_plan_lgmap_host(petiga_cuda_plan* P, int* lgmap) {
+  if (!P || !lgmap) return PETIGA_CUDA_ERR_ARG;
+  memcpy(lgmap, P->L.lgmap.data(), P->L.lgmap.size() * sizeof(int));
+  return 0;
+}
+
+int petiga_cuda_plan_pattern(petiga_cuda_plan* P, int block, int* nrows, int64_t* nnz, const int** d_rowptr, const int** d_colidx) {
+  if (!P || (block != 0 && block != 1)) return PETIGA_CUDA_ERR_ARG;
+  const Layout& L = P->L;
+  const int bs = block ? 1 : L.dof;
+  const int64_t n = L.nnz_own * bs * bs;
+  if (n > INT32_MAX) { set_error("pattern: more than 2^31-1 nonzeros on one rank; use the block (BAIJ) layout or more ranks"); return PETIGA_CUDA_ERR_SUP; }
+  PC_CUDA(cudaSetDevice(P->device));
+  if (!P->d_rowptr[block]) {
+    std::vector<int> rp((size_t)L.nown * bs + 1);
+    rp[0] = 0;
+    for (int r = 0; r < L.nown; r++) {
+      int W = L.rowW[0][r] * L.rowW[1][r] * L.rowW[2][r];
+      for (int k = 0; k < bs; k++) rp[(size_t)r * bs + k + 1] = (int)(L.rowbase[r] * bs * bs + (int64_t)(k + 1) * W * bs);
+    }
+    PC_CUDA(cudaMalloc(&P->d_rowptr[block], rp.size() * sizeof(int)));
+    PC_CUDA(cudaMemcpyAsync(P->d_rowptr[block], rp.data(), rp.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
+    PC_CUDA(cudaMalloc(&P->d_colidx[block], (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    PatParams pp;
+    for (int d = 0; d < 3; d++) {
+      pp.rowG[d] = P->d_rowG[d]; pp.W[d] = P->dax[d].W; pp.seg[d] = P->dax[d].seg; pp.first[d] = P->d_first[d]; pp.own[d] = P->d_own[d];
+      pp.box_ls[d] = P->d_box_ls[d]; pp.box_lw[d] = P->d_box_lw[d]; pp.gs[d] = L.ax[d].gs; pp.nnp[d] = L.ax[d].nnp; pp.Pn[d] = L.ax[d].P;
+    }
+    pp.rank_start = P->d_rank_start; pp.rowbase = P->d_rowbase; pp.nown = L.nown; pp.bs = bs; pp.colidx = P->d_colidx[block];
+    const int blocks = std::max(1, std::min((L.nown + 7) / 8, P->num_sms * 16));
+    pattern_kernel<<<blocks, 256, 0, P->stream>>>(pp);
+    PC_CUDA(cudaGetLastError());
+    P->launches++;
+    PC_CUDA(cudaStreamSynchronize(P->stream));
+  }
+  if (nrows) *nrows = L.nown * bs;
+  if (nnz) *nnz = n;
+  if (d_rowptr) *d_rowptr = P->d_rowptr[block];
+  if (d_colidx) *d_colidx = P->d_colidx[block];
+  return 0;
+}
+
+int petiga_cuda_plan_pattern_host(petiga_cuda_plan* P, int block, int* rowptr, int* colidx) {
+  int nrows = 0; int64_t nnz = 0; const int *drp, *dci;
+  int rc = petiga_cuda_plan_pattern(P, block, &nrows, &nnz, &drp, &dci);
+  if (rc) return rc;
+  if (rowptr) PC_CUDA(cudaMemcpy(rowptr, drp, ((size_t)nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (colidx) PC_CUDA(cudaMemcpy(colidx, dci, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure(double** buf, size_t* cap, size_t n) {
+  if (*cap >= n && *buf) return 0;
+  cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  PC_CUDA(cudaMalloc(buf, (n ? n : 1) * sizeof(double)));
+  *cap = n;
+  return 0;
+}
+
+int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, const double* V, double t, const double* U,
+                        double* values, double* rhs) {
+  if (!P || slot < 0 || slot >= PETIGA_NSLOTS || (block != 0 && block != 1)) return PETIGA_CUDA_ERR_ARG;
+  const Layout& L = P->L;
+  const int form = P->slots[slot].form;
+  if (form < 0) { set_error("compute: no form selected for this slot (IGACheckFormOp)"); return PETIGA_CUDA_ERR_ORDER; }
+  FormInfo fi = form_info(form, slot, L.dim, L.dof);
+  if (!fi.valid) return PETIGA_CUDA_ERR_SUP;
+  const bool want_mat = (slot == PETIGA_SLOT_MATRIX || slot == PETIGA_SLOT_SYSTEM || slot == PETIGA_SLOT_JACOBIAN || slot == PETIGA_SLOT_IJACOBIAN);
+  const bool want_vec = (slot == PETIGA_SLOT_VECTOR || slot == PETIGA_SLOT_SYSTEM || slot == PETIGA_SLOT_FUNCTION || slot == PETIGA_SLOT_IFUNCTION);
+  const bool state = (slot >= PETIGA_SLOT_FUNCTION);
+  const bool transient = (slot == PETIGA_SLOT_IFUNCTION || slot == PETIGA_SLOT_IJACOBIAN);
+  if (want_mat && !values) { set_error("compute: values == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (want_vec && !rhs) { set_error("compute: rhs == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (state && !U) { set_error("compute: U == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (transient && !V) { set_error("compute: V == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (fi.order > P->order) { set_error("compute: form reads derivatives above IGASetOrder"); return PETIGA_CUDA_ERR_ARG; }
+  PC_CUDA(cudaSetDevice(P->device));
+  const int bs2 = L.dof * L.dof;
+  const size_t nval = (size_t)L.nnz_own * bs2, nvec = (size_t)L.nown * L.dof;
+  const bool multi = L.nranks > 1;
+
+  // path selection
+  const bool kron_ok = kron_applicable(P, slot, form);
+  if (P->path == PETIGA_PATH_KRONECKER && !kron_ok) { set_error("compute: separable path not applicable (geometry, state or non-separable form)"); return PETIGA_CUDA_ERR_SUP; }
+  const bool use_kron = kron_ok && P->path != PETIGA_PATH_QUADRATURE;
+  P->last_path = use_kron ? PETIGA_PATH_KRONECKER : PETIGA_PATH_QUADRATURE;
+
+  cudaEventRecord(P->ev0, P->stream);
+  if (use_kron) {   // write-once path: no zeroing, no atomics, no exchange
+    int rc = launch_kronecker(P, slot, block, want_mat ? values : nullptr, want_vec ? rhs : nullptr);
+    cudaEventRecord(P->ev1, P->stream);
+    return rc;
+  }
+
+  // MatZeroEntries / VecZeroEntries (petigaksp.c:166-167)
+  if (want_mat) PC_CUDA(cudaMemsetAsync(values, 0, nval * sizeof(double), P->stream));
+  double* rhs_k = rhs;
+  if (multi) {
+    if (want_mat) {
+      int rc = ensure(&P->d_ghost_values, &P->ghost_values_cap, (size_t)(L.nnz_loc - L.nnz_own) * bs2);
+      if (rc) return rc;
+      PC_CUDA(cudaMemsetAsync(P->d_ghost_values, 0, (size_t)(L.nnz_loc - L.nnz_own) * bs2 * sizeof(double), P->stream));
+    }
+    if (want_vec) { rhs_k = P->d_rhs_loc; PC_CUDA(cudaMemsetAsync(rhs_k, 0, (size_t)L.nloc * L.dof * sizeof(double), P->stream)); }
+  } else if (want_vec) PC_CUDA(cudaMemsetAsync(rhs, 0, nvec * sizeof(double), P->stream));
+
+  // IGAGetLocalVecArray: G2L halo of the state (petigavec.c:256-269)
+  const double *U_k = U, *V_k = V;
+  if (multi && state) {
+    int rc = halo_state(P, U, P->d_U_loc);
+    if (rc) return rc;
+    U_k = P->d_U_loc;
+    if (transient) { rc = halo_state(P, V, P->d_V_loc); if (rc) return rc; V_k = P->d_V_loc; }
+  }
+
+  if (P->d_X && fi.order > 1) { set_error("compute: second derivatives on a mapped geometry are not available on the device path yet"); return PETIGA_CUDA_ERR_SUP; }
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  for (int d = 0; d < 3; d++) kp.ax[d] = P->dax[d];
+  kp.dim = L.dim; kp.dof = L.dof;
+  kp.nelem = L.ax[0].ew * L.ax[1].ew * L.ax[2].ew;
+  kp.nown = L.nown; kp.nnz_own = L.nnz_own;
+  kp.localrow = P->d_localrow; kp.rowbase = P->d_rowbase;
+  kp.values = values; kp.ghost_values = P->d_ghost_values; kp.rhs = rhs_k;
+  kp.U = state ? U_k : nullptr; kp.V = transient ? V_k : nullptr;
+  kp.X = P->d_X; kp.Wt = P->d_W; kp.fixtable = P->d_fixtable;
+  kp.any_bc = 0;
+  const bool apply_bc = (slot != PETIGA_SLOT_VECTOR && slot != PETIGA_SLOT_MATRIX);   // IGAComputeVector/Matrix never fix (petigaksp.c:33-139)
+  if (P->has_bc && apply_bc)
+    for (int d = 0; d < L.dim; d++)
+      for (int s = 0; s < 2; s++) {
+        FixSide& fs = kp.bc[d][s];
+        for (int k = 0; k < P->bc.vcount[d][s]; k++) {
+          int c = P->bc.vfield[d][s][k];
+          if (c >= L.dof) continue;   // AddFixa skips fields >= dof (petigaelem.c:1179)
+          fs.vfield[fs.vcount] = c; fs.vvalue[fs.vcount] = P->bc.vvalue[d][s][k]; fs.vcount++;
+        }
+        for (int k = 0; k < P->bc.lcount[d][s]; k++) {
+          int c = P->bc.lfield[d][s][k];
+          if (c >= L.dof) continue;
+          fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
+        }
+        if (fs.vcount || fs.lcount) kp.any_bc = 1;
+        if (fs.lcount && P->d_X) { set_error("compute: boundary loads on a mapped geometry (BoundaryArea) are not available on the device path yet"); return PETIGA_CUDA_ERR_SUP; }
+      }
+  kp.form = form; kp.slot = slot; kp.block = block;
+  kp.mc0 = fi.mc0; kp.mc1 = fi.mc1; kp.vc0 = fi.vc0; kp.vc1 = fi.vc1;
+  kp.per_qp = fi.per_qp; kp.needs_x = fi.needs_x; kp.needs_state = fi.needs_state || (state && kp.any_bc);
+  int c0 = 99, c1 = 0;
+  if (fi.mc1 > fi.mc0) { c0 = std::min(c0, fi.mc0); c1 = std::max(c1, fi.mc1); }
+  if (fi.vc1 > fi.vc0) { c0 = std::min(c0, fi.vc0); c1 = std::max(c1, fi.vc1); }
+  if (c1 == 0) { c0 = 0; c1 = 1; }
+  if (P->d_X) { c0 = 0; c1 = std::max(c1, 1 + L.dim); }
+  if (kp.needs_state) c0 = std::min(c0, 0), c1 = std::max(c1, 1);
+  kp.c0 = c0; kp.c1 = c1;
+  memcpy(kp.prm, P->slots[slot].prm, sizeof(kp.prm));
+  kp.shift = shift; kp.t = t;
+  int rc = launch_quadrature(P, kp);
+  if (rc) return rc;
+  cudaEventRecord(P->ev1, P->stream);
+  if (multi) {
+    rc = exchange_ghost_rows(P, block, values, rhs, want_mat, want_vec);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int petiga_cuda_finish(petiga_cuda_plan* P) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  PC_CUDA(cudaSetDevice(P->device));
+  PC_CUDA(cudaStreamSynchronize(P->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) P->last_kernel_ms = ms;
+  else (void)cudaGetLastError();
+  return 0;
+}
+
+int petiga_cuda_compute_host(petiga_cuda_plan* P, int slot, int block, double shift, const double* V_host, double t,
+                             const double* U_host, double* values_host, double* rhs_host) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  const Layout& L = P->L;
+  PC_CUDA(cudaSetDevice(P->device));
+  const size_t nval = (size_t)L.nnz_own * L.dof * L.dof, nvec = (size_t)L.nown * L.dof;
+  size_t cap;
+  if (values_host) { int rc = ensure(&P->d_values_own, &P->values_own_cap, nval); if (rc) return rc; }
+  cap = P->d_rhs_own ? nvec : 0; { int rc = ensure(&P->d_rhs_own, &cap, nvec); if (rc) return rc; }
+  if (U_host) { cap = P->d_U_own ? nvec : 0; int rc = ensure(&P->d_U_own, &cap, nvec); if (rc) return rc;
+    PC_CUDA(cudaMemcpyAsync(P->d_U_own, U_host, nvec * sizeof(double), cudaMemcpyHostToDevice, P->stream)); }
+  if (V_host) { cap = P->d_V_own ? nvec : 0; int rc = ensure(&P->d_V_own, &cap, nvec); if (rc) return rc;
+    PC_CUDA(cudaMemcpyAsync(P->d_V_own, V_host, nvec * sizeof(double), cudaMemcpyHostToDevice, P->stream)); }
+  int rc = petiga_cuda_compute(P, slot, block, shift, V_host ? P->d_V_own : nullptr, t, U_host ? P->d_U_own : nullptr,
+                               values_host ? P->d_values_own : nullptr, rhs_host ? P->d_rhs_own : nullptr);
+  if (rc) return rc;
+  if (values_host) PC_CUDA(cudaMemcpyAsync(values_host, P->d_values_own, nval * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  if (rhs_host) PC_CUDA(cudaMemcpyAsync(rhs_host, P->d_rhs_own, nvec * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  return petiga_cuda_finish(P);
+}
+
+// ---- small device-memory helpers ----
+int petiga_cuda_malloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaMalloc(ptr, bytes ? bytes : 1)); return 0; }
+int petiga_cuda_free(void* ptr) { PC_CUDA(cudaFree(ptr)); return 0; }
+int petiga_cuda_memcpy_h2d(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int petiga_cuda_memcpy_d2h(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int petiga_cuda_host_alloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1)); return 0; }
+int petiga_cuda_host_free(void* ptr) { PC_CUDA(cudaFreeHost(ptr)); return 0; }
+
+int petiga_cuda_plan_exchange_info(petiga_cuda_plan* P, int kind, int* count, int* out, int capacity) {
+  if (!P || !count) return PETIGA_CUDA_ERR_ARG;
+  const Layout& L = P->L;
+  if (kind == 0) {
+    *count = (int)L.send.size();
+    if (out) for (int i = 0; i < *count && i < capacity; i++) { out[3 * i] = L.send[i].rank; out[3 * i + 1] = L.send[i].first_row; out[3 * i + 2] = L.send[i].nrows; }
+  } else {
+    *count = (int)L.recv.size();
+    if (out) for (int i = 0; i < *count && i < capacity; i++) { out[3 * i] = L.recv[i].rank; out[3 * i + 1] = L.recv[i].rows.empty() ? -1 : L.recv[i].rows[0]; out[3 * i + 2] = (int)L.recv[i].rows.size(); }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// pc_device.h -- device-resident plan tables and kernel parameter blocks (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "pc_forms.cuh"
+#include "pc_layout.h"
+
+namespace pc {
+
+struct DevAxis {
+  const double* value;    // [nel][nqp][nen][5]   IGABasis.value (include/petiga.h:122-141)
+  const double* weight;   // [nel][nqp]
+  const double* point;    // [nel][nqp]
+  const double* detJac;   // [nel]
+  const int* offset;      // [nel]
+  const int* W;           // [gw]  1-D row width by ghost coordinate
+  const int* lo;          // [gw]  row coordinate - first column
+  const uint32_t* seg;    // [gw][kMaxW] packed (B | S<<8 | L<<16)
+  int nel, nqp, nen, p, gs, gw, es, ew, periodic, nnp;
+};
+
+struct FixSide {          // IGAFormBC value/load of one face, restricted to fields < dof
+  int vcount, lcount;
+  int vfield[kMaxDof];
+  double vvalue[kMaxDof];
+  int lfield[kMaxDof];
+  double lvalue[kMaxDof];
+};
+
+struct KParams {
+  DevAxis ax[3];
+  int dim, dof;
+  int nelem;                       // local elements
+  int nown;                        // owned rows
+  int64_t nnz_own;                 // blocks in owned rows
+  const int* localrow;             // [ghost box] -> local row
+  const int64_t* rowbase;          // [nloc+1]
+  double* values;                  // owned rows (caller's array)
+  double* ghost_values;            // ghost rows (plan's buffer), indexed from block nnz_own
+  double* rhs;                     // [nloc*dof] unified local vector (owned first)
+  const double* U;                 // [nloc*dof] unified local state (owned first) or NULL
+  const double* V;
+  const double* X;                 // geometry [ghost box][dim] or NULL
+  const double* Wt;                // rational weights [ghost box] or NULL
+  const double* fixtable;          // [ghost box][dof] or NULL
+  FixSide bc[3][2];
+  int any_bc;
+  int form, slot, block;           // block: 1 = BAIJ value layout, 0 = AIJ
+  int mc0, mc1, vc0, vc1, per_qp, needs_x, needs_state;
+  int c0, c1;                      // tabulated component range (union)
+  double prm[8];
+  double shift, t;
+  int qc;                          // quadrature points per chunk
+  int epb;                         // elements per block
+};
+
+}  // namespace pc

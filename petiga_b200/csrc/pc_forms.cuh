@@ -1,0 +1,196 @@
+// pc_forms.cuh -- built-in device forms as per-quadrature-point coefficient tensors.
+//
+// The reference calls a host callback per quadrature point that fills K[a][i][b][j] and F[a][i] with an
+// O(nen^2) double loop (e.g. demo/Poisson3D.c:3-23).  Every built-in form is bilinear in the tabulated
+// shape quantities Psi = (N, dN/dx_0.., Laplacian N) of the test function a and the trial function b:
+//      K_q[a,i,b,j] = sum_{al,be} Psi_al(a) * C_q[i][j][al][be] * Psi_be(b)
+//      F_q[a,i]     = sum_{al}    Psi_al(a) * f_q[i][al]
+// so on the device a form is only the small generator of (C_q, f_q); the O(nen^2 nqp) work is one
+// form-independent FP64 contraction (pc_quad.cuh).  The algebra is the reference's expression
+// re-associated; parity is checked to 1e-12 relative Frobenius error, not bit-wise.
+//
+// Psi component numbering: 0 = N, 1..DIM = first derivatives, DIM+1 = Laplacian.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/petiga_cuda.h"
+
+namespace pc {
+
+constexpr int kMaxComp = 5;   // N, 3 derivatives, Laplacian
+constexpr int kMaxDof = 4;
+
+// static description of a (form, slot) pair: which Psi components the matrix / vector parts read
+struct FormInfo {
+  int valid;          // form provides this slot
+  int mc0, mc1;       // matrix component range [mc0, mc1)
+  int vc0, vc1;       // vector component range [vc0, vc1)
+  int per_qp;         // coefficients depend on the quadrature point (state / position)
+  int needs_x;        // reads the physical point
+  int needs_state;    // reads U (and V for transient slots)
+  int order;          // highest derivative read (0, 1 or 2)
+  int constant_f;     // vector coefficient is a constant (eligible for the separable path)
+};
+
+__host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int dof) {
+  FormInfo f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool lin = (slot == PETIGA_SLOT_VECTOR || slot == PETIGA_SLOT_MATRIX || slot == PETIGA_SLOT_SYSTEM);
+  const bool fun = (slot == PETIGA_SLOT_FUNCTION || slot == PETIGA_SLOT_IFUNCTION);
+  const bool jac = (slot == PETIGA_SLOT_JACOBIAN || slot == PETIGA_SLOT_IJACOBIAN);
+  switch (form) {
+    case PETIGA_FORM_POISSON:
+      if (dof != 1) break;
+      if (lin) { f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 1; f.order = 1; f.constant_f = 1; }
+      else if (slot == PETIGA_SLOT_FUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      else if (slot == PETIGA_SLOT_JACOBIAN) { f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.order = 1; f.needs_state = 1; }
+      break;
+    case PETIGA_FORM_LAPLACE:
+      if (dof != 1 || !lin) break;
+      f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 0; f.order = 1; f.constant_f = 1;
+      break;
+    case PETIGA_FORM_L2PROJECTION:
+      if (dof != 1 || !lin) break;
+      f.valid = 1; f.mc0 = 0; f.mc1 = 1; f.vc0 = 0; f.vc1 = 1; f.per_qp = 1; f.needs_x = 1; f.order = 0;
+      break;
+    case PETIGA_FORM_MASS:
+      if (!lin || dof > kMaxDof) break;
+      f.valid = 1; f.mc0 = 0; f.mc1 = 1; f.vc0 = 0; f.vc1 = 1; f.order = 0; f.constant_f = 1;
+      break;
+    case PETIGA_FORM_ELASTICITY3D:
+      if (!lin || dim != 3 || dof != 3) break;
+      f.valid = 1; f.mc0 = 1; f.mc1 = 4; f.vc0 = 0; f.vc1 = 0; f.order = 1; f.constant_f = 1;
+      break;
+    case PETIGA_FORM_ELASTICITY:
+      if (!lin || dof != dim) break;
+      f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 0; f.order = 1; f.constant_f = 1;
+      break;
+    case PETIGA_FORM_CAHNHILLIARD2D:
+      if (dim != 2 || dof != 1) break;
+      if (slot == PETIGA_SLOT_IFUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 4; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
+      if (slot == PETIGA_SLOT_IJACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 4; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
+      break;
+    case PETIGA_FORM_BRATU:
+      if (dof != 1) break;
+      if (fun) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      if (jac) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      break;
+  }
+  if (slot == PETIGA_SLOT_VECTOR) { f.mc0 = f.mc1 = 0; }
+  if (slot == PETIGA_SLOT_MATRIX) { f.vc0 = f.vc1 = 0; }
+  return f;
+}
+
+// demo/L2Projection.c:3-61
+__device__ inline double l2_function(int choice, int dim, const double* x) {
+  double f = 0;
+  switch (choice) {
+    case 0: for (int i = 0; i < dim; i++) f += x[i]; return f;
+    case 1: for (int i = 0; i < dim; i++) f += x[i] * x[i]; return f;
+    case 2: for (int i = 0; i < dim; i++) f += x[i] * x[i] * x[i]; return f;
+    case 3: for (int i = 0; i < dim; i++) f += x[i] * x[i] * x[i] * x[i]; return f;
+    case 4: {
+      double X = 2.5 * x[0] + 1, Y = 2.0 * (dim > 1 ? x[1] : 0.0) + 0;
+      return exp(-X * X - Y * Y) + 0.5 * exp(-(X - 2) * (X - 2) - (Y - 0.5) * (Y - 0.5));
+    }
+    case 5: {
+      double X = x[0] * 3, Y = (dim > 1 ? x[1] : 0.0) * 3;
+      return 3 * pow(1 - X, 2) * exp(-pow(X, 2) - pow(Y + 1, 2)) - 10 * (X / 5 - pow(X, 3) - pow(Y, 5)) * exp(-pow(X, 2) - pow(Y, 2)) -
+             1.0 / 3 * exp(-pow(X + 1, 2) - pow(Y, 2));
+    }
+    case 6: f = 1; for (int i = 0; i < dim; i++) f *= sin(M_PI * x[i]); return f;
+    case 7: for (int i = 0; i < dim; i++) f += (x[i] < 0.0) ? -1.0 : +1.0; return f;
+  }
+  return 0;
+}
+
+// What a form sees at one quadrature point (the device "IGAPoint": include/petiga.h:644-703)
+struct QPoint {
+  double x[3];          // physical point (IGAPointFormGeomMap)
+  double u[kMaxDof];    // IGAPointFormValue(U)
+  double v[kMaxDof];    // IGAPointFormValue(V)
+  double gu[kMaxDof][3];// IGAPointFormGrad(U)
+  double d2u[kMaxDof];  // IGAPointFormDel2(U)
+};
+
+// Fill the coefficient tensors of one quadrature point.
+//   C : [DOF][DOF][NA][NA]  (NA = mc1-mc0), index ((i*DOF+j)*NA+al)*NA+be, components relative to mc0
+//   fv: [DOF][NV]           (NV = vc1-vc0), index i*NV+al, components relative to vc0
+// Both are pre-zeroed by the caller.
+template <int DIM, int DOF>
+__device__ inline void form_coefficients(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
+                                         int NA, int NV, double* C, double* fv) {
+  (void)t;
+  switch (form) {
+    case PETIGA_FORM_POISSON:   // demo/Poisson3D.c:18,20 ; residual/tangent of the same problem for SNES slots
+      if (C && NA) for (int d = 0; d < DIM; d++) C[d * NA + d] = 1.0;
+      if (fv && NV) {
+        if (slot == PETIGA_SLOT_FUNCTION) { fv[0] = -1.0; for (int d = 0; d < DIM; d++) fv[1 + d] = q.gu[0][d]; }
+        else fv[0] = 1.0;
+      }
+      break;
+    case PETIGA_FORM_LAPLACE:   // demo/Laplace.c:44-45
+      if (C && NA) for (int d = 0; d < DIM; d++) C[d * NA + d] = 1.0;
+      break;
+    case PETIGA_FORM_L2PROJECTION:  // demo/L2Projection.c:81-85
+      if (C && NA) C[0] = 1.0;
+      if (fv && NV) fv[0] = l2_function((int)prm[0], DIM, q.x);
+      break;
+    case PETIGA_FORM_MASS:      // test/IGACreate.c:24-41
+      if (C && NA) for (int i = 0; i < DOF; i++) C[(i * DOF + i) * NA * NA] = 1.0;
+      if (fv && NV) for (int i = 0; i < DOF; i++) fv[i * NV] = 1.0;
+      break;
+    case PETIGA_FORM_ELASTICITY3D: {  // demo/Elasticity3D.c:33-41, literal (note the mu*mu of :37)
+      if (!(C && NA) || DIM != 3 || DOF != 3) break;
+      const double la = prm[0], mu = prm[1];
+#define CE(i, j, al, be) C[(((i) * DOF + (j)) * NA + (al)) * NA + (be)]
+      CE(0, 0, 0, 0) = la + 2 * mu; CE(0, 0, 1, 1) = mu; CE(0, 0, 2, 2) = mu;
+      CE(0, 1, 0, 1) = la; CE(0, 1, 1, 0) = mu;
+      CE(0, 2, 0, 2) = la; CE(0, 2, 2, 0) = mu;
+      CE(1, 0, 0, 1) = mu; CE(1, 0, 1, 0) = la;
+      CE(1, 1, 1, 1) = la + 2 * mu; CE(1, 1, 2, 2) = mu; CE(1, 1, 0, 0) = mu * mu;
+      CE(1, 2, 1, 2) = la; CE(1, 2, 2, 1) = mu;
+      CE(2, 0, 0, 2) = mu; CE(2, 0, 2, 0) = la;
+      CE(2, 1, 1, 2) = mu; CE(2, 1, 2, 1) = la;
+      CE(2, 2, 0, 0) = mu; CE(2, 2, 1, 1) = mu; CE(2, 2, 2, 2) = la + 2 * mu;
+      break;
+    }
+    case PETIGA_FORM_ELASTICITY: {    // demo/Elasticity.c:36-44
+      if (!(C && NA) || DOF != DIM) break;
+      const double la = prm[0], mu = prm[1];
+      for (int i = 0; i < DOF; i++)
+        for (int j = 0; j < DOF; j++)
+          for (int al = 0; al < DIM; al++)
+            for (int be = 0; be < DIM; be++)
+              CE(i, j, al, be) = (i == j && al == be ? mu : 0.0) + (al == i && be == j ? la : 0.0) + (al == j && be == i ? mu : 0.0);
+      break;
+    }
+#undef CE
+    case PETIGA_FORM_CAHNHILLIARD2D: {  // demo/CahnHilliard2D.c:9-32,84-197
+      const double theta = prm[0], alpha = prm[1];
+      const double c = q.u[0], c_t = q.v[0], c_x = q.gu[0][0], c_y = q.gu[0][1], del2_c = q.d2u[0];
+      const double M = c * (1 - c), dM = 1 - 2 * c, d2M = -2;
+      double dmu = 0.5 / theta * 1 / (c * (1 - c)) - 2; dmu *= 3 * alpha;
+      const double t1 = M * dmu + dM * del2_c;
+      if (fv && NV) { fv[0] = c_t; fv[1] = c_x * t1; fv[2] = c_y * t1; fv[3] = M * del2_c; }
+      if (C && NA) {
+        double d2mu = 0.5 / theta * (2 * c - 1) / (c * c * (1 - c) * (1 - c)); d2mu *= 3 * alpha;
+        const double t2 = (dM * dmu + M * d2mu + d2M * del2_c);
+        C[0 * NA + 0] = shift;
+        C[1 * NA + 1] = t1; C[2 * NA + 2] = t1;
+        C[1 * NA + 0] = c_x * t2; C[1 * NA + 3] = c_x * dM;
+        C[2 * NA + 0] = c_y * t2; C[2 * NA + 3] = c_y * dM;
+        C[3 * NA + 0] = dM * del2_c; C[3 * NA + 3] = M;
+      }
+      break;
+    }
+    case PETIGA_FORM_BRATU: {   // demo/BratuFJ.F90:22-62 (Function), :64-114 (Jacobian), :118-150 (IFunction), IJacobian
+      const double lam = prm[0], eu = exp(q.u[0]);
+      const bool tr = (slot == PETIGA_SLOT_IFUNCTION || slot == PETIGA_SLOT_IJACOBIAN);
+      if (fv && NV) { fv[0] = (tr ? q.v[0] : 0.0) - lam * eu; for (int d = 0; d < DIM; d++) fv[1 + d] = q.gu[0][d]; }
+      if (C && NA) { C[0] = (tr ? shift : 0.0) - lam * eu; for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = 1.0; }
+      break;
+    }
+  }
+}
+
+}  // namespace pc

@@ -1,0 +1,91 @@
+// pc_plan.h -- the plan object behind the C ABI (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "pc_device.h"
+
+struct petiga_cuda_plan {
+  pc::Layout L;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  void* nccl = nullptr;           // ncclComm_t
+  int order = 1;
+
+  // host copies needed later
+  std::vector<double> detJac_h[3];
+  std::vector<int> first_h[3];
+
+  // device tables
+  pc::DevAxis dax[3];
+  std::vector<void*> allocs;      // everything cudaMalloc'ed by the plan (freed on destroy)
+  int* d_localrow = nullptr;
+  int64_t* d_rowbase = nullptr;
+  int* d_rowG[3] = {nullptr, nullptr, nullptr};
+  int* d_first[3] = {nullptr, nullptr, nullptr};
+  int* d_own[3] = {nullptr, nullptr, nullptr};
+  int* d_box_ls[3] = {nullptr, nullptr, nullptr};
+  int* d_box_lw[3] = {nullptr, nullptr, nullptr};
+  int* d_rank_start = nullptr;
+  // 1-D element matrices for the separable path: [comp pair][nel][nen][nen]
+  double* d_kron1d[3] = {nullptr, nullptr, nullptr};
+  double* d_kronrow[3] = {nullptr, nullptr, nullptr};   // 1-D global banded matrices [4][nnp][kMaxW]
+
+  // pattern (owned by the plan), per block mode
+  int* d_rowptr[2] = {nullptr, nullptr};
+  int* d_colidx[2] = {nullptr, nullptr};
+
+  // geometry / bc / state
+  double* d_X = nullptr;
+  double* d_W = nullptr;
+  double* d_fixtable = nullptr;
+  petiga_cuda_bc bc;
+  bool has_bc = false;
+  // unified local buffers (multi-rank) and exchange staging
+  double* d_ghost_values = nullptr; size_t ghost_values_cap = 0;
+  double* d_rhs_loc = nullptr;     // [nloc*dof]
+  double* d_U_loc = nullptr;       // [nloc*dof]
+  double* d_V_loc = nullptr;
+  double* d_recv = nullptr; size_t recv_cap = 0;
+  int* d_recv_rows = nullptr;      // concatenated recv row lists
+  std::vector<size_t> recv_row_off;
+  // host staging for *_host entry points
+  double* h_pinned = nullptr; size_t h_pinned_cap = 0;
+  double* d_values_own = nullptr; size_t values_own_cap = 0;   // device arrays used by compute_host
+  double* d_rhs_own = nullptr;
+  double* d_U_own = nullptr;
+  double* d_V_own = nullptr;
+
+  struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
+  int path = PETIGA_PATH_AUTO;
+  int scatter = 0;
+  // stats
+  long launches = 0;
+  int last_path = 0;
+  double last_kernel_ms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 148;
+};
+
+namespace pc {
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define PC_CUDA(call)                                              \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    if (_e != cudaSuccess) return pc::cuda_fail(_e, #call);        \
+  } while (0)
+
+// quadrature path (pc_quad.cu)
+int launch_quadrature(petiga_cuda_plan* P, const KParams& base);
+// separable path (pc_kron.cu)
+bool kron_applicable(const petiga_cuda_plan* P, int slot, int form);
+int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, double* rhs);
+// ghost exchange (pc_comm.cu)
+int exchange_ghost_rows(petiga_cuda_plan* P, int block, double* values, double* rhs, bool mat, bool vec);
+int halo_state(petiga_cuda_plan* P, const double* U_own, double* U_loc);
+int nccl_load();
+}  // namespace pc

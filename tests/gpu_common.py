@@ -1,0 +1,70 @@
+"""GPU-side helpers: run one assembly through the host mirror (C-ABI underneath) and through the oracle."""
+import numpy as np
+
+from tests.common import oracle_to_layout, rel_frobenius
+
+MAT_SLOTS = ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN")
+VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION")
+
+
+def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None):
+    g = g or case.product()
+    if path is not None:
+        g.SetOption("path", {"auto": 0, "quadrature": 1, "kronecker": 2}[path])
+    g.SetForm(slot, form, params)
+    A = g.CreateMat() if slot in MAT_SLOTS else None
+    B = g.CreateVec() if slot in VEC_SLOTS else None
+    vU = vV = vT = None
+    if fixtable is not None:
+        vT = g.CreateVec(); vT.set(fixtable); g.SetFixTable(vT)
+    if U is not None:
+        vU = g.CreateVec(); vU.set(U)
+    if V is not None:
+        vV = g.CreateVec(); vV.set(V)
+    if slot == "VECTOR": g.ComputeVector(B)
+    elif slot == "MATRIX": g.ComputeMatrix(A)
+    elif slot == "SYSTEM": g.ComputeSystem(A, B)
+    elif slot == "FUNCTION": g.ComputeFunction(vU, B)
+    elif slot == "JACOBIAN": g.ComputeJacobian(vU, A)
+    elif slot == "IFUNCTION": g.ComputeIFunction(shift, vV, t, vU, B)
+    elif slot == "IJACOBIAN": g.ComputeIJacobian(shift, vV, t, vU, A)
+    out = dict(path=int(g.GetStat("last_path")), g=g)
+    if A is not None:
+        out["rowptr"], out["colidx"] = A.pattern()
+        out["values"] = A.values()
+        out["baij"] = A.baij
+    if B is not None:
+        out["rhs"] = B.get()
+    for v in (A, B, vU, vV, vT):
+        if v is not None:
+            v.destroy()
+    return out
+
+
+def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12):
+    """Pattern bit-exact; values / vectors within `tol` relative Frobenius error (north_star: 1e-12)."""
+    o = case.oracle()
+    if fixtable is not None:
+        o.fixtable(fixtable)
+    o.setup()
+    Ko, Fo = o.assemble(slot, form, params, shift=shift, V=V, t=t, U=U)
+    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable)
+    rp_o, ci_o, _ = o.pattern()
+    errs = {}
+    if Ko is not None:
+        dof = case.dof
+        if res["baij"] or dof == 1:
+            assert np.array_equal(res["rowptr"], rp_o) and np.array_equal(res["colidx"], ci_o)
+        else:
+            assert len(res["rowptr"]) - 1 == (len(rp_o) - 1) * dof and len(res["colidx"]) == len(ci_o) * dof * dof
+        exp = oracle_to_layout(Ko, rp_o, dof, res["baij"])
+        errs["K"] = rel_frobenius(res["values"], exp)
+        assert errs["K"] <= tol, ("matrix", errs["K"])
+    if Fo is not None:
+        errs["F"] = rel_frobenius(res["rhs"], Fo.reshape(-1))
+        scale = np.linalg.norm(Fo)
+        if scale == 0:
+            assert np.abs(res["rhs"]).max() == 0
+        else:
+            assert errs["F"] <= tol, ("vector", errs["F"])
+    return res, errs

@@ -1,0 +1,224 @@
+"""GPU parity tests: libpetiga_cuda (through the host mirror of the reference API) against the CPU oracle on the
+same inputs.  Pattern and numbering bit-exact; values within 1e-12 relative Frobenius error (BASELINE north_star)."""
+import numpy as np
+import pytest
+
+from tests.common import Case, state_vectors
+from tests.gpu_common import check_against_oracle, run_product
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def dirichlet_all(dim, value=1.0, field=0):
+    return [(d, s, field, value) for d in range(dim) for s in range(2)]
+
+
+# ---- F1 Poisson (BASELINE cfg 1 and 2 at reduced mesh) --------------------------------------------------
+@pytest.mark.parametrize("dim,p,N", [(1, 1, 9), (1, 2, 8), (1, 3, 7), (1, 4, 6), (2, 1, 7), (2, 2, 9), (2, 3, 6), (2, 4, 5),
+                                     (3, 1, 5), (3, 2, 6), (3, 3, 6), (3, 4, 4)])
+@pytest.mark.parametrize("path", ["quadrature", "auto"])
+def test_poisson_system(dim, p, N, path):
+    case = Case(dim, p=p, N=N, bcv=dirichlet_all(dim))
+    check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL)
+
+
+def test_poisson2d_cfg1_full_size():
+    """BASELINE configs[0]: Poisson2D p=2 64x64, IGAComputeSystem."""
+    case = Case(2, p=2, N=64, bcv=dirichlet_all(2))
+    for path in ("quadrature", "auto"):
+        check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL)
+
+
+@pytest.mark.parametrize("C", [0, 1])
+def test_poisson_lower_continuity_and_rules(C):
+    case = Case(2, p=3, N=5, C=C, q=(5, 4), bcv=dirichlet_all(2, 0.5))
+    check_against_oracle(case, "SYSTEM", "POISSON", path="quadrature", tol=TOL)
+    check_against_oracle(case, "SYSTEM", "POISSON", path="auto", tol=TOL)
+
+
+# ---- F2 Laplace: value on side 0, zero load on side 1 (demo/Laplace.c:108-113) ---------------------------
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("path", ["quadrature", "auto"])
+def test_laplace_system(dim, path):
+    bcv = [(d, 0, 0, 1.0) for d in range(dim)]
+    bcl = [(d, 1, 0, 0.0) for d in range(dim)]
+    check_against_oracle(Case(dim, p=2, N=6, bcv=bcv, bcl=bcl), "SYSTEM", "LAPLACE", path=path, tol=TOL)
+
+
+# ---- F3 L2 projection, all eight right-hand sides (demo/L2Projection.c:3-61), cfg 3 at reduced mesh -------
+@pytest.mark.parametrize("choice", range(8))
+def test_l2projection_functions(choice):
+    check_against_oracle(Case(2, p=2, N=7, limits=(-1.0, 1.0)), "SYSTEM", "L2PROJECTION", params=[choice], tol=TOL)
+
+
+@pytest.mark.parametrize("path", ["quadrature", "auto"])
+def test_l2projection_3d_p4(path):
+    check_against_oracle(Case(3, p=4, N=4, limits=(-1.0, 1.0)), "SYSTEM", "L2PROJECTION", params=[0], path=path, tol=TOL)
+
+
+# ---- mass form of test/IGACreate.c: all three linear drivers, dof 1-3, AIJ and BAIJ, periodic mixes --------
+@pytest.mark.parametrize("dim,dof,periodic,N", [(1, 1, False, 8), (2, 2, False, 6), (2, 3, (True, False), (10, 5)), (3, 1, True, 10),
+                                                (3, 2, False, 4), (3, 3, (False, True, False), (4, 10, 3))])
+@pytest.mark.parametrize("mattype", ["aij", "baij"])
+def test_mass_matrix_vector_system(dim, dof, periodic, N, mattype):
+    case = Case(dim, dof=dof, p=2, N=N, periodic=periodic, mattype=mattype)
+    for slot in ("SYSTEM", "MATRIX", "VECTOR"):
+        for path in ("quadrature", "auto"):
+            check_against_oracle(case, slot, "MASS", path=path, tol=TOL)
+
+
+# ---- F4 Elasticity3D (cfg 4 at reduced mesh), BAIJ default and AIJ --------------------------------------
+@pytest.mark.parametrize("mattype", [None, "aij"])
+@pytest.mark.parametrize("path", ["quadrature", "auto"])
+def test_elasticity3d(mattype, path):
+    bcv = [(0, 0, 0, 0.0), (0, 0, 1, 0.0), (0, 0, 2, 0.0), (0, 1, 0, 1.0)]      # demo/Elasticity3D.c:67-70
+    case = Case(3, dof=3, p=2, N=(5, 4, 4), bcv=bcv, mattype=mattype)
+    res, _ = check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[1.0, 1.0], path=path, tol=TOL)
+    check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[2.5, 0.7], path=path, tol=TOL)   # exercises the mu*mu term
+
+
+# ---- F5 Elasticity (dim-generic) with a Neumann load: AddFlux / BoundaryArea ------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("path", ["quadrature", "auto"])
+def test_elasticity_generic_with_load(dim, path):
+    bcv = [(0, 0, i, 0.0) for i in range(dim)]
+    bcl = [(0, 1, i, [1.0, 0.5, -0.25][i]) for i in range(dim)]
+    case = Case(dim, dof=dim, p=2, N=5, order=1, bcv=bcv, bcl=bcl)
+    check_against_oracle(case, "SYSTEM", "ELASTICITY", params=[1.0, 1.0], path=path, tol=TOL)   # ctx {mu, lambda}
+
+
+# ---- F6 CahnHilliard2D (cfg 5 at reduced mesh): IFunction + IJacobian with state ---------------------------
+@pytest.mark.parametrize("N", [8, 32])
+def test_cahnhilliard2d(N):
+    case = Case(2, p=2, N=N, C=1, periodic=True)
+    n = N * N
+    U, V = state_vectors(n)
+    prm = [1.5, 3000.0]
+    check_against_oracle(case, "IFUNCTION", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL)
+    check_against_oracle(case, "IJACOBIAN", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL)
+
+
+# ---- SNES / TS drivers with Dirichlet data: Bratu and the Poisson residual --------------------------------
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_bratu_function_jacobian(dim):
+    case = Case(dim, p=2, N=5, bcv=dirichlet_all(dim, 0.0))
+    o = case.oracle(); o.setup()
+    n = len(o.pattern()[0]) - 1
+    U, V = state_vectors(n)
+    check_against_oracle(case, "FUNCTION", "BRATU", [6.8], U=U, tol=TOL)
+    check_against_oracle(case, "JACOBIAN", "BRATU", [6.8], U=U, tol=TOL)
+    check_against_oracle(case, "IFUNCTION", "BRATU", [6.8], U=U, V=V, shift=2.0, tol=TOL)
+    check_against_oracle(case, "IJACOBIAN", "BRATU", [6.8], U=U, V=V, shift=2.0, tol=TOL)
+
+
+def test_poisson_function_jacobian_nonzero_dirichlet():
+    case = Case(2, p=3, N=5, bcv=dirichlet_all(2, 0.75))
+    o = case.oracle(); o.setup()
+    n = len(o.pattern()[0]) - 1
+    U, _ = state_vectors(n)
+    check_against_oracle(case, "FUNCTION", "POISSON", U=U, tol=TOL)
+    check_against_oracle(case, "JACOBIAN", "POISSON", U=U, tol=TOL)
+
+
+# ---- Dirichlet data from a vector (IGASetFixTable, test/IGAFixTable.c) --------------------------------------
+def test_fixtable():
+    case = Case(2, p=2, N=6, bcv=dirichlet_all(2, 0.0))
+    o = case.oracle(); o.setup()
+    n = len(o.pattern()[0]) - 1
+    table = np.cos(np.arange(n) * 0.37)
+    check_against_oracle(case, "SYSTEM", "POISSON", fixtable=table, path="quadrature", tol=TOL)
+    check_against_oracle(case, "SYSTEM", "POISSON", fixtable=table, path="auto", tol=TOL)
+
+
+# ---- mapped geometry (K5-K7) and NURBS (K4) ------------------------------------------------------------
+@pytest.mark.parametrize("dim,p,N", [(2, 2, 6), (2, 3, 5), (3, 2, 4), (3, 3, 4)])
+def test_mapped_geometry_poisson(dim, p, N):
+    case = Case(dim, p=p, N=N, geometry=("perturbed", 0.05), bcv=dirichlet_all(dim))
+    res, _ = check_against_oracle(case, "SYSTEM", "POISSON", tol=TOL)
+    assert res["path"] == 1     # mapped geometry can only take the quadrature path
+
+
+def test_mapped_geometry_elasticity_and_mass():
+    case = Case(3, dof=3, p=2, N=3, geometry=("perturbed", 0.04), bcv=[(0, 0, i, 0.0) for i in range(3)])
+    check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[1.0, 1.0], tol=TOL)
+    case = Case(2, dof=2, p=2, N=5, geometry=("perturbed", 0.05))
+    check_against_oracle(case, "SYSTEM", "MASS", tol=TOL)
+
+
+@pytest.mark.parametrize("form,params", [("POISSON", []), ("L2PROJECTION", [6]), ("MASS", [])])
+def test_nurbs_quarter_annulus(form, params):
+    """Refined quarter annulus of test/IGAGeometryMap.c:18-32 (rational weights => Rationalize path)."""
+    import petiga_b200 as pb
+    from oracle.oracle import OracleIGA
+    from tests.geomutil import refine_annulus
+    from tests.common import rel_frobenius
+    o, X, W = refine_annulus(OracleIGA, N=(5, 6))
+    for d in range(2):
+        o.boundary_value(d, 0, 0, 1.0)
+    o.setup()
+    Ko, Fo = o.assemble("SYSTEM", form, params)
+    g, _, _ = refine_annulus(pb.IGA, N=(5, 6))
+    for d in range(2):
+        g.SetBoundaryValue(d, 0, 0, 1.0)
+    g.SetUp()
+    g.SetForm("SYSTEM", form, params)
+    A, B = g.CreateMat(), g.CreateVec()
+    g.ComputeSystem(A, B)
+    rp, ci = A.pattern()
+    rpo, cio, _ = o.pattern()
+    assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+    assert rel_frobenius(A.values(), Ko.reshape(-1)) <= TOL
+    assert rel_frobenius(B.get(), Fo.reshape(-1)) <= TOL
+    if form == "MASS":
+        assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6      # area of the quarter annulus
+
+
+# ---- size-independent properties at BASELINE's full cfg-2 size (the oracle cannot run 128^3 in seconds) -------
+def test_cfg2_full_size_properties():
+    import petiga_b200 as pb
+    N, p = 128, 3
+    g = pb.IGA(3, 1)
+    for d in range(3):
+        g.AxisInitUniform(d, p, N)
+    g.SetUp()
+    for d in range(3):
+        for s in range(2):
+            g.SetBoundaryValue(d, s, 0, 1.0)
+    g.SetForm("SYSTEM", "POISSON")
+    A, B = g.CreateMat(), g.CreateVec()
+    assert A.nrows == 131 ** 3 and A.nnz == 905 ** 3 == 741217625          # SURVEY 8 size table
+    sums = {}
+    for path in ("auto", "quadrature"):
+        g.SetOption("path", {"auto": 0, "quadrature": 1}[path])
+        g.ComputeSystem(A, B)
+        rhs = B.get()
+        # total load: sum F = volume of free part + Dirichlet rows count*value; compare both paths + closed forms
+        sums[path] = rhs
+    assert np.allclose(sums["auto"], sums["quadrature"], rtol=1e-12, atol=1e-15)
+    rhs = sums["auto"].reshape(131, 131, 131)
+    # a corner node sits in 1 element, an edge node next to it in 2, a face-interior node in up to 16 (4x4)
+    assert rhs[0, 0, 0] == 1.0 and rhs[0, 0, 1] == 2.0 and rhs[0, 0, 2] == 3.0 and rhs[0, 0, 64] == 4.0
+    assert rhs[0, 64, 64] == 16.0
+    # sample rows of the matrix through the device pattern: interior row sums of a stiffness matrix vanish,
+    # fixed rows are count * identity
+    import ctypes as C
+    plan = g.plan()
+    L = pb.load_cuda()
+    rp = np.empty(A.nrows + 1, dtype=np.int32)
+    L.petiga_cuda_plan_pattern_host(plan, 0, rp.ctypes.data_as(C.POINTER(C.c_int)), None)
+    vals_ptr = A.device_ptr()
+    def row_values(r):
+        n = int(rp[r + 1] - rp[r])
+        out = np.empty(n)
+        L.petiga_cuda_memcpy_d2h(out.ctypes.data_as(C.c_void_p), C.c_void_p(vals_ptr + 8 * int(rp[r])), C.c_size_t(8 * n))
+        return out
+    idx = lambda i, j, k: i + 131 * (j + 131 * k)
+    v = row_values(idx(64, 64, 64))
+    assert len(v) == 343 and abs(v.sum()) < 1e-12 * np.abs(v).sum()
+    v = row_values(idx(5, 70, 9))
+    assert abs(v.sum()) < 1e-12 * np.abs(v).sum()
+    v = row_values(idx(0, 64, 64))
+    assert np.count_nonzero(v) == 1 and v.sum() == 16.0
+    A.destroy(); B.destroy()

@@ -1,0 +1,143 @@
+"""CPU tests of the product's host logic against the oracle: 1-D tables, partition, numbering (lgmap) and the
+closed-form CSR pattern must be bit-exact.  No GPU needed: petiga_layout_* is host code."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import petiga_b200 as pb
+from oracle.oracle import partition as oracle_partition
+from tests.common import Case
+
+CASES = [
+    Case(1, p=1, N=5), Case(1, p=2, N=7, C=0), Case(1, p=3, N=16, periodic=True), Case(1, p=4, N=9, C=1),
+    Case(2, p=2, N=(8, 5)), Case(2, p=3, N=6, C=(2, 0)), Case(2, p=2, N=10, periodic=True), Case(2, p=(2, 3), N=(7, 6)),
+    Case(2, dof=3, p=2, N=(10, 5), periodic=(True, False)), Case(3, p=2, N=6), Case(3, p=3, N=(5, 4, 6)), Case(3, p=1, N=4),
+    Case(3, dof=3, p=2, N=4), Case(3, p=2, N=(6, 10, 6), periodic=(False, True, False)), Case(3, p=4, N=5, C=2),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_p%s_N%s_C%s_w%s_dof%d" % (c.dim, c.p, c.N, c.C, c.periodic, c.dof))
+@pytest.mark.parametrize("size", [1, 2, 3, 4, 8])
+def test_tables_numbering_pattern_bit_exact(case, size):
+    o = case.oracle()
+    Nel = [case.N[d] if isinstance(case.N, tuple) else case.N for d in range(case.dim)]
+    try:
+        grid, _ = oracle_partition(size, 0, case.dim, Nel)
+    except AssertionError:
+        pytest.skip("partition too fine")
+    if any(isinstance(case.periodic, tuple) and case.periodic[d] or case.periodic is True for d in range(case.dim)):
+        # a periodic axis needs every rank box wider than the stencil; skip over-decomposed tiny meshes
+        if any(Nel[d] // grid[d] < 2 * (case.p[d] if isinstance(case.p, tuple) else case.p) + 1 for d in range(case.dim)) and size > 1:
+            pytest.skip("periodic mesh too small for this rank count")
+    rp_o, ci_o, rs_o = o.pattern(size)
+    for rank in range(size):
+        inf_o = o.setup(size, rank)
+        g = case.product(rank=rank, size=size)
+        inf_p = g.info()
+        assert inf_p == inf_o
+        assert pb.iga_partition(size, rank, case.dim, Nel) == oracle_partition(size, rank, case.dim, Nel)
+        for d in range(case.dim):
+            to, tp = o.tables(d), g.tables(d)
+            for k in ("U", "detJac", "weight", "point"):
+                assert np.array_equal(to[k], tp[k]), k          # bit-exact knots / rule / Jacobians
+            assert np.array_equal(to["value"], tp["value"])      # same algorithm, same operation order
+        assert np.array_equal(g.lgmap(), o.lgmap())
+        L = g.layout()
+        assert np.array_equal(L.lgmap(), o.lgmap())
+        # block pattern of this rank's rows == the oracle's rows [rs[rank], rs[rank+1])
+        rp, ci = L.pattern(1, case.dof)
+        r0, r1 = rs_o[rank], rs_o[rank + 1]
+        assert len(rp) - 1 == r1 - r0
+        assert np.array_equal(rp, rp_o[r0:r1 + 1] - rp_o[r0])
+        assert np.array_equal(ci, ci_o[rp_o[r0]:rp_o[r1]])
+        if case.dof > 1:   # AIJ expansion: UnblockIndices (petigamat.c:303-314)
+            rps, cis = L.pattern(0, case.dof)
+            dof = case.dof
+            assert len(rps) - 1 == (r1 - r0) * dof
+            for r in range(0, r1 - r0, max(1, (r1 - r0) // 7)):
+                cols = ci[rp[r]:rp[r + 1]]
+                exp = (cols[:, None] * dof + np.arange(dof)[None, :]).reshape(-1)
+                for c in range(dof):
+                    row = r * dof + c
+                    assert np.array_equal(cis[rps[row]:rps[row + 1]], exp)
+
+
+def test_exchange_lists_are_consistent():
+    """Ghost rows sent by rank s to rank r must be exactly the rows r expects from s, in the same order."""
+    case, size = Case(3, p=2, N=6), 8
+    lays, infos = [], []
+    for rank in range(size):
+        g = case.product(rank=rank, size=size)
+        lays.append((g, g.layout()))
+    for r, (g, L) in enumerate(lays):
+        lg, lr = L.lgmap(), L.localrow()
+        nown = L.sizes()["nown"]
+        glob_of_local = {}
+        for gnode, row in zip(lg, lr):
+            glob_of_local[row] = gnode
+        for (peer, first, nrows, nblocks) in L.exchange(0):
+            Lp = lays[peer][1]
+            recv = Lp.exchange(1)
+            idx = [i for i in range(len(recv)) if recv[i][0] == r]
+            assert len(idx) == 1
+            rows = Lp.recv_rows(idx[0], int(recv[idx[0]][2]))
+            assert len(rows) == nrows and recv[idx[0]][3] == nblocks
+            peer_start = None
+            # global ids must match one to one
+            lgp, lrp = Lp.lgmap(), Lp.localrow()
+            own_glob = {row: gn for gn, row in zip(lgp, lrp) if row < Lp.sizes()["nown"]}
+            for t in range(nrows):
+                assert glob_of_local[first + t] == own_glob[rows[t]]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library must export every function include/petiga_cuda.h declares (no compute calls here)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = pb.load_cuda()
+    H = pb.load_host()
+    names = re.findall(r"\b(petiga_(?:cuda|layout)_\w+)\s*\(", open(os.path.join(root, "include", "petiga_cuda.h")).read())
+    assert len(set(names)) >= 30
+    for n in set(names):
+        assert hasattr(L, n), n
+    hnames = re.findall(r"^PetscErrorCode\s+(\w+)\s*\(", open(os.path.join(root, "include", "petiga_host.h")).read(), re.M)
+    assert len(set(hnames)) >= 50
+    for n in set(hnames):
+        assert hasattr(H, n), n
+    assert L.petiga_cuda_version() == 100
+
+
+def test_error_behaviour_matches_reference_checks():
+    g = pb.IGA()
+    with pytest.raises(pb.IGAError) as e:
+        g.SetUp()                                   # "Must call IGASetDim() first" (petiga.c:1458)
+    assert e.value.code == 73
+    g.SetDim(2)
+    with pytest.raises(pb.IGAError):
+        g.SetDim(4)
+    with pytest.raises(pb.IGAError) as e:
+        g.AxisInitUniform(0, 2, 0)                  # petigaaxis.c:414
+    assert e.value.code == 62
+    with pytest.raises(pb.IGAError) as e:
+        g.SetBoundaryValue(3, 0, 0, 1.0)            # IGAFormCheckArg (petigaform.c:95-99)
+    assert e.value.code == 63
+    # a host callback cannot be a device form
+    CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+    cb = CB(lambda p, K, F, ctx: 0)
+    with pytest.raises(pb.IGAError) as e:
+        g.SetFormRaw("SYSTEM", cb)
+    assert e.value.code == 56
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU every device entry point must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = Case(2, p=2, N=4).product()
+    g.SetForm("SYSTEM", "POISSON")
+    with pytest.raises(pb.IGAError) as e:
+        g.CreateMat()
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
