@@ -164,7 +164,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
     }
     for (int t = lt; t < 3 * NEN1 * NEN1; t += G) {
       int d = t / (NEN1 * NEN1), r = t - d * NEN1 * NEN1, ia = r / NEN1, ib = r - ia * NEN1;
-      uint32_t s = 0x00010100u;   // unused axis: B=0,S=1,L=0
+      uint32_t s = 0x00000100u;   // unused axis: B=0,S=1,L=0
       if (d < DIM) {
         int g = prm.ax[d].offset[ID[d]] + ia - prm.ax[d].gs;
         int c = ib - ia + prm.ax[d].lo[g];
@@ -258,8 +258,8 @@ quad_kernel(const __grid_constant__ KParams prm) {
         }
       }
       __syncthreads();
-      if (valid && lt < nq) {  // K6 InverseMap order 1 (petigamapinv.f90.in:28-31, petigadet/inv.f90.in)
-        double* J = X1 + lt * DIM * DIM;   // J[i][d]
+      if (valid) for (int ql = lt; ql < nq; ql += G) {  // K6 InverseMap order 1 (petigamapinv.f90.in:28-31, petigadet/inv.f90.in)
+        double* J = X1 + ql * DIM * DIM;   // J[i][d]
         double E[DIM * DIM], det;
         if (DIM == 1) { det = J[0]; E[0] = 1.0 / det; }
         else if (DIM == 2) {
@@ -272,7 +272,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
           E[3] = -(a10 * a22 - a12 * a20) / det; E[4] = (a00 * a22 - a02 * a20) / det; E[5] = -(a00 * a12 - a02 * a10) / det;
           E[6] = (a10 * a21 - a11 * a20) / det; E[7] = -(a00 * a21 - a01 * a20) / det; E[8] = (a00 * a11 - a01 * a10) / det;
         }
-        detX[lt] = det;
+        detX[ql] = det;
 #pragma unroll
         for (int k = 0; k < DIM * DIM; k++) J[k] = E[k];
       }
@@ -315,8 +315,8 @@ quad_kernel(const __grid_constant__ KParams prm) {
       __syncthreads();
     }
     // per-point weights and coefficient tensors
-    if (valid && lt < nq) {
-      int q = q0 + lt;
+    if (valid) for (int ql = lt; ql < nq; ql += G) {
+      int q = q0 + ql;
       int qi[3] = {q % nq1[0], (q / nq1[0]) % nq1[1], q / (nq1[0] * nq1[1])};
       double w = 1.0, J = 1.0;
       QPoint qp;
@@ -329,26 +329,26 @@ quad_kernel(const __grid_constant__ KParams prm) {
         qp.x[d] = prm.ax[d].point[ID[d] * nq1[d] + qi[d]];
       }
       if (mapped) {
-        J *= Geo[QC * DIM * DIM + lt];      // detJac *= detX (petigaelem.c:1024-1029)
+        J *= Geo[QC * DIM * DIM + ql];      // detJac *= detX (petigaelem.c:1024-1029)
 #pragma unroll
-        for (int d = 0; d < DIM; d++) qp.x[d] = Xq[lt * 3 + d];
+        for (int d = 0; d < DIM; d++) qp.x[d] = Xq[ql * 3 + d];
       }
       const double jw = J * w;              // IGAPointAddArray: JW = detJac*weight (petigapoint.c:461)
-      JW[lt] = jw;
+      JW[ql] = jw;
       if (prm.per_qp || q0 == 0) {
         if (state) {
           const int per = DOF * (2 + DIM + 1);
 #pragma unroll
           for (int i = 0; i < DOF; i++) {
-            const double* s = Sq + lt * per + i * (2 + DIM + 1);
+            const double* s = Sq + ql * per + i * (2 + DIM + 1);
             qp.u[i] = s[0]; qp.v[i] = s[1];
 #pragma unroll
             for (int d = 0; d < DIM; d++) qp.gu[i][d] = s[2 + d];
             qp.d2u[i] = s[2 + DIM];
           }
         }
-        double* C = Cq + (size_t)lt * DOF * DOF * NA * NA;
-        double* fv = Fq + (size_t)lt * DOF * (NV > 0 ? NV : 1);
+        double* C = Cq + (size_t)ql * DOF * DOF * NA * NA;
+        double* fv = Fq + (size_t)ql * DOF * (NV > 0 ? NV : 1);
         for (int k = 0; k < DOF * DOF * NA * NA; k++) C[k] = 0.0;
         for (int k = 0; k < DOF * NV; k++) fv[k] = 0.0;
         form_coefficients<DIM, DOF>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, NA, NV, NA ? C : nullptr, NV ? fv : nullptr);
