@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- element-assembly throughput of libpetiga_cuda on BASELINE.json's headline configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--path auto|quadrature] [--mesh 128]
+
+Workload (config.workload): demo/Poisson3D of the reference, p=3 C2, 128^3 elements, dof=1, AIJ, Dirichlet 1.0 on
+all six faces, one `IGAComputeSystem` per step (zero -> integrate -> fix-up -> scatter -> fully assembled).
+metric = assembled Mnnz/s (scalar nonzeros of the assembled matrix / time of one assembly); elements/s is reported
+beside it.  N > 1 (torchrun, one rank per GPU): the same global mesh split by the reference's box partition
+(strong scaling), value = global nnz / max-over-ranks time.
+
+--impl reference times the CPU restatement of the reference's assembly (oracle/, "port": the reference needs
+PETSc+MPI+gfortran and cannot be built here) on all host cores, one emulated MPI rank per core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NNZ_FULL, NEL_FULL = 741217625, 128 ** 3       # cfg 2
+W_E = 64 * (4096 * 7 + 64 * 3)                 # algorithmic FLOP per element, SURVEY.md 8(d)
+FP64_NOMINAL_TFLOPS = 37.2                     # 148 SM x 64 DFMA lanes x 2 x 1.965 GHz
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for (ts, line) in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(mesh, p=3):
+    from tests.common import Case
+    return Case(3, p=p, N=mesh, bcv=[(d, s, 0, 1.0) for d in range(3) for s in range(2)])
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, threads=None, per_rank=None, native=True):
+    """Oracle ("port") timed on host cores: T processes = T emulated MPI ranks of the reference's box partition,
+    each integrating its own element box of a bounded sample mesh (per_rank^3 elements per rank)."""
+    import multiprocessing as mp
+    from oracle.oracle import partition
+    T = threads or os.cpu_count() or 1
+    T = max(1, T)
+    per_rank = per_rank or 12
+    grid, _ = partition(T, 0, 3, [per_rank * T] * 3)     # reference's own processor grid for T ranks
+    mesh = [per_rank * g for g in grid]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(T, initializer=_cpu_worker_init, initargs=(mesh, T, native)) as pool:
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker_step, range(T))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    nel = mesh[0] * mesh[1] * mesh[2]
+    sec = sum(times) / len(times)
+    el_s = nel / sec
+    return dict(seconds=sec, elements=nel, elements_per_s=el_s, mnnz_per_s=el_s * NNZ_FULL / NEL_FULL / 1e6, cores=T, mesh=mesh,
+                sample="Poisson3D p=3 C2 on a %dx%dx%d sub-mesh (%d^3 elements per emulated rank, %d ranks as processes, "
+                       "reference box partition), one IGAComputeSystem element loop per step; Mnnz/s = elements/s x "
+                       "(741217625 nnz / 2097152 elements of the full 128^3 mesh)" % (mesh[0], mesh[1], mesh[2], per_rank, T))
+
+
+_W = {}
+
+
+def _cpu_worker_init(mesh, T, native):
+    import numpy as np
+    from oracle.oracle import OracleIGA
+    o = OracleIGA(3, 1, native=native)
+    for d in range(3):
+        o.axis_uniform(d, 3, mesh[d])
+        for s in range(2):
+            o.boundary_value(d, s, 0, 1.0)
+    rp, ci, _ = o.pattern(T)
+    _W.update(o=o, T=T, vals=np.zeros((len(ci), 1, 1)), rhs=np.zeros((len(rp) - 1, 1)))
+
+
+def _cpu_worker_step(rank):
+    _W["vals"][:] = 0
+    _W["rhs"][:] = 0
+    _W["o"].assemble_rank("SYSTEM", "POISSON", [], _W["T"], rank, _W["vals"], _W["rhs"])
+    return 0
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, args.warmup, threads=args.cpu_threads)
+    line = {
+        "impl": "reference", "metric": "assembled_Mnnz_per_s", "value": r["mnnz_per_s"], "unit": "Mnnz/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "elements_per_s": r["elements_per_s"],
+        "config": {"workload": "demo/Poisson3D p=3 C2 128^3 dof=1 AIJ IGAComputeSystem (CPU sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--path", default="auto", choices=["auto", "quadrature"])
+    ap.add_argument("--mesh", type=int, default=128)
+    ap.add_argument("--cpu-threads", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import ctypes as C
+    import numpy as np
+    import torch
+    import petiga_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libpetiga_cuda has no CPU fallback")
+    torch.cuda.set_device(local)
+    L = pb.load_cuda()
+    nccl = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            assert L.petiga_cuda_comm_unique_id(raw) == 0, L.petiga_cuda_last_error()
+            idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        comm = C.c_void_p()
+        assert L.petiga_cuda_comm_init(C.byref(comm), world, rank, raw, local) == 0, L.petiga_cuda_last_error()
+        nccl = comm.value
+
+    stream = torch.cuda.Stream()
+    case = build_case(args.mesh)
+    g = case.product(rank=rank, size=world, nccl=nccl, device=local, setup=False)
+    g.SetStream(stream.cuda_stream)
+    g.SetUp()
+    g.SetOption("path", {"auto": 0, "quadrature": 1}[args.path])
+    g.SetForm("SYSTEM", "POISSON")
+    A, B = g.CreateMat(), g.CreateVec()          # IGACreateMat: pattern built once, outside the timed region
+    nnz_local = A.nnz
+    nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_global = int(nnz_t.item())
+    nel_global = args.mesh ** 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            g.ComputeSystem(A, B)
+        path_used = int(g.GetStat("last_path"))
+        # -------- timed region: device-resident (inputs already in HBM) --------
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        barrier()
+        l0 = g.GetStat("launches")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        kern_ms = 0.0
+        for _ in range(args.steps):
+            g.ComputeSystem(A, B)
+            kern_ms += g.GetStat("last_kernel_ms")
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = int(g.GetStat("launches") - l0)
+        if t1 - t0 < 1.0:      # too short for nvidia-smi to see: keep the same kernel busy ~1.5 s for the clock record only
+            tend = time.time() + 1.5
+            while time.time() < tend:
+                g.ComputeSystem(A, B)
+            t1 = time.time()
+        clocks = sampler.stop(t0, t1)
+        kern_ms /= args.steps
+
+    ms_t = torch.tensor([ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms, kern_ms = float(ms_t[0]), float(ms_t[1])
+
+    # -------- end-to-end through the C-ABI with HOST buffers (pinned), D2H of the assembled system inside --------
+    e2e = None
+    if not args.no_e2e:
+        plan = g.plan()
+        nval, nvec = A.nnz, B.size
+        hv, hr = C.c_void_p(), C.c_void_p()
+        assert L.petiga_cuda_host_alloc(C.byref(hv), C.c_size_t(nval * 8)) == 0
+        assert L.petiga_cuda_host_alloc(C.byref(hr), C.c_size_t(nvec * 8)) == 0
+        ksteps = max(2, min(args.steps, 5))
+        L.petiga_cuda_compute_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        bc = _bc_struct(case)
+        with torch.cuda.stream(stream):
+            for it in range(1 + ksteps):
+                if it == 1:
+                    barrier()
+                    e0.record(stream)
+                rc = L.petiga_cuda_set_bc(plan, C.byref(bc))          # this step's inputs: the BC tables, host -> device
+                assert rc == 0
+                rc = L.petiga_cuda_compute_host(plan, 2, 0, 0.0, None, 0.0, None, hv, hr)
+                assert rc == 0, L.petiga_cuda_last_error()
+            e1.record(stream)
+            barrier()
+        ms_e = torch.tensor([e0.elapsed_time(e1) / ksteps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        chk = float(np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_double)), shape=(nvec,))[:8].sum())
+        e2e = {"value": nnz_global / (float(ms_e[0]) * 1e-3) / 1e6, "unit": "Mnnz/s", "ms_per_step": float(ms_e[0]),
+               "h2d_bytes_per_step": C.sizeof(bc), "d2h_bytes_per_step": (nval + nvec) * 8, "steps": ksteps, "rhs_checksum8": chk}
+        L.petiga_cuda_host_free(hv); L.petiga_cuda_host_free(hr)
+
+    if rank != 0:
+        return 0
+    peaks = measured_peaks()
+    sec = ms * 1e-3
+    value = nnz_global / sec / 1e6
+    if path_used == 2:     # separable path: one write-once kernel, HBM bound
+        alg_bytes = 8.0 * (nnz_local + B.size)
+        roof = {"bound": "hbm", "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                "traffic": None, "kernel": "kron_rows_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+    else:                  # quadrature path: FP64 FMA bound; achieved = W_e x elements / kernel time
+        flop = float(W_E) * (nel_global / world)
+        roof = {"bound": "fp64", "achieved": flop / (kern_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                "traffic": None, "kernel": "quad_kernel<3,3,1,4>", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
+                "peak_source": "nominal FP64 FMA peak (148 SM x 64 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no FP64 figure"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {
+        "metric": "assembled_Mnnz_per_s", "value": value, "unit": "Mnnz/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "elements_per_s": nel_global / sec,
+        "config": {"workload": "demo/Poisson3D p=3 C2 %d^3 dof=1 AIJ IGAComputeSystem" % args.mesh, "elements": nel_global, "nnz": nnz_global,
+                   "path": {1: "quadrature", 2: "kronecker"}.get(path_used, str(path_used)),
+                   "l2": "each step rewrites the %.2f GB value array (> 126 MB L2)" % (nnz_local * 8 / 1e9),
+                   "parallelism": "box partition, %d rank(s)" % world},
+        "clocks": clocks, "gpu_launches": launches, "roofline": roof,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 1, threads=1, per_rank=16)
+        line["cpu_baseline"] = {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": 1, "kind": "port", "sample": r["sample"],
+                                "elements_per_s": r["elements_per_s"]}
+    print(json.dumps(line))
+    return 0
+
+
+def _bc_struct(case):
+    import ctypes as C
+
+    class BC(C.Structure):
+        _fields_ = [("vcount", (C.c_int * 2) * 3), ("vfield", ((C.c_int * 64) * 2) * 3), ("vvalue", ((C.c_double * 64) * 2) * 3),
+                    ("lcount", (C.c_int * 2) * 3), ("lfield", ((C.c_int * 64) * 2) * 3), ("lvalue", ((C.c_double * 64) * 2) * 3),
+                    ("fixtableU", C.c_void_p)]
+    bc = BC()
+    for (a, s, f, v) in case.bcv:
+        k = bc.vcount[a][s]
+        bc.vfield[a][s][k] = f
+        bc.vvalue[a][s][k] = v
+        bc.vcount[a][s] = k + 1
+    return bc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -146,6 +146,8 @@ PetscErrorCode IGAGetBasisTable(IGA iga, PetscInt axis, PetscInt which, PetscRea
 PetscErrorCode IGAGetLGMapHost(IGA iga, PetscInt *lgmap);
 PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* forwarded to petiga_cuda_set_option */
 PetscErrorCode IGAGetStat(IGA iga, const char *name, PetscReal *value);
+PetscErrorCode IGASetStream(IGA iga, void *cuda_stream);                      /* stream all device work is enqueued on */
+void *IGAGetLayout(IGA iga);                                                 /* the petiga_layout behind the IGA */
 PetscErrorCode IGAGetPlan(IGA iga, void **plan);                             /* the petiga_cuda_plan behind the IGA */
 const char *IGAGetLastErrorMessage(void);
 /* pure host logic (no GPU needed): partition of src/petigapart.c */

@@ -76,6 +76,8 @@ def lib(native=False):
         getattr(L, name).argtypes = [C.c_void_p]
     L.oiga_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
                                 C.c_void_p, _dp, _dp]
+    L.oiga_assemble_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
+                                     C.c_void_p, _dp, _dp]
     L.oiga_tabulate_element.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 12
     if not native:
         _LIB = L
@@ -180,6 +182,14 @@ class OracleIGA:
         ci = np.ctypeslib.as_array(self.L.oiga_pattern_colidx(p), shape=(nnz,)).copy()
         rs = np.ctypeslib.as_array(self.L.oiga_pattern_rank_rowstart(p), shape=(size + 1,)).copy()
         return rp, ci, rs
+
+    def assemble_rank(self, slot, form, params, size, rank, vals, rhs, shift=0.0, V=None, t=0.0, U=None):
+        """Element loop of one emulated rank into preallocated global arrays (CPU-baseline timing)."""
+        self.pattern(size)
+        prm = np.ascontiguousarray(list(params) + [0.0] * 4, dtype=np.float64)
+        rc = self.L.oiga_assemble_rank(self.h, size, rank, SLOT[slot], FORM[form], _d(prm), shift, _d(V), t, _d(U),
+                                       self._pat[size], _d(vals), _d(rhs))
+        assert rc == 0, rc
 
     def assemble(self, slot, form, params=(), size=1, shift=0.0, V=None, t=0.0, U=None):
         """Returns (values[nnzb, dof, dof] or None, rhs[nrows, dof] or None) of one full assembly."""

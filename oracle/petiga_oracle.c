@@ -1134,7 +1134,7 @@ static long csr_find(const GlobalPattern *gp, int row, int col) /* the sorted-ro
 /* One full assembly over `size` emulated ranks.
    values: [nnz_blocks][dof][dof] (row-major blocks), rhs: [nrows][dof]; either may be NULL per slot.
    Ug/Vg: global vectors (PETSc ordering) or NULL.  Returns 0, or >0 on error (e.g. entry outside pattern). */
-static int assemble(OIGA *o, int size, int slot, int form, const double *prm, double shift, const double *Vg,
+static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const double *prm, double shift, const double *Vg,
                     double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
 {
   int r, dof = o->dof, err = 0;
@@ -1143,7 +1143,7 @@ static int assemble(OIGA *o, int size, int slot, int form, const double *prm, do
   int state = (slot >= SLOT_FUNCTION), transient = (slot == SLOT_IFUNCTION || slot == SLOT_IJACOBIAN);
   if (want_mat) memset(values, 0, sizeof(double)*(size_t)gp->nnz*dof*dof);   /* MatZeroEntries */
   if (want_vec) memset(rhs, 0, sizeof(double)*(size_t)gp->nrows*dof);        /* VecZeroEntries */
-  for (r = 0; r < size && !err; r++) {
+  for (r = r0; r < r1 && !err; r++) {
     Elem e; int index, count, N, ng; double *A, *B, *K, *F, *U = NULL, *V = NULL, *arrayU = NULL, *arrayV = NULL;
     if (setup_rank(o, size, r)) return 1;
     elem_alloc(&e, o);
@@ -1317,7 +1317,12 @@ const int *oiga_pattern_rank_rowstart(const GlobalPattern *gp) { return gp->rank
 
 int oiga_assemble(OIGA *o, int size, int slot, int form, const double *prm, double shift, const double *Vg,
                   double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
-{ return assemble(o, size, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
+{ return assemble(o, size, 0, size, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
+/* the element loop of ONE emulated rank (its contributions only, into the global arrays): lets the CPU baseline run
+   the ranks in parallel processes the way mpiexec -n size would */
+int oiga_assemble_rank(OIGA *o, int size, int rank, int slot, int form, const double *prm, double shift, const double *Vg,
+                       double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
+{ return assemble(o, size, rank, rank+1, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
 
 /* Tabulate one element of the current rank (after oiga_setup) for the geometry known-answer tests.
    out arrays sized by the caller: weight[nqp], detJac[nqp] (already *detX), detX[nqp], point[nqp][dim],

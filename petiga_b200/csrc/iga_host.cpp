@@ -70,6 +70,7 @@ struct _p_IGA {
   struct Slot { int form = -1; double prm[8] = {0}; int nprm = 0; bool dirty = false; } slots[PETIGA_NSLOTS];
   petiga_layout* layout = nullptr;
   petiga_cuda_plan* plan = nullptr;
+  void* stream = nullptr;
   std::vector<std::pair<std::string, double>> options;
 };
 
@@ -193,7 +194,7 @@ PetscErrorCode ensure_plan(IGA g) {
   if (!g->plan) {
     petiga_cuda_space sp;
     fill_space(g, sp);
-    int rc = petiga_cuda_plan_create(&g->plan, &sp, g->comm.rank, g->comm.size, g->comm.nccl, nullptr, g->comm.device);
+    int rc = petiga_cuda_plan_create(&g->plan, &sp, g->comm.rank, g->comm.size, g->comm.nccl, g->stream, g->comm.device);
     if (rc) return from_cuda(rc);
     g->bc_dirty = g->geom_dirty = true;
     for (auto& s : g->slots) s.dirty = (s.form >= 0);
@@ -708,5 +709,11 @@ PetscErrorCode IGAGetPlan(IGA g, void** plan) {
   return 0;
 }
 void* IGAGetLayout(IGA g) { return g ? g->layout : nullptr; }
+PetscErrorCode IGASetStream(IGA g, void* stream) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (g->plan) return fail(PETSC_ERR_ORDER, "IGASetStream must be called before the first IGACreateMat/Vec/Compute");
+  g->stream = stream;
+  return 0;
+}
 
 }  // extern "C"

@@ -42,7 +42,7 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       if (dof != 1) break;
       if (lin) { f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 1; f.order = 1; f.constant_f = 1; }
       else if (slot == PETIGA_SLOT_FUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
-      else if (slot == PETIGA_SLOT_JACOBIAN) { f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.order = 1; f.needs_state = 1; }
+      else if (slot == PETIGA_SLOT_JACOBIAN) { f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.order = 1; }
       break;
     case PETIGA_FORM_LAPLACE:
       if (dof != 1 || !lin) break;
@@ -81,7 +81,7 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
 }
 
 // demo/L2Projection.c:3-61
-__device__ inline double l2_function(int choice, int dim, const double* x) {
+__host__ __device__ inline double l2_function(int choice, int dim, const double* x) {
   double f = 0;
   switch (choice) {
     case 0: for (int i = 0; i < dim; i++) f += x[i]; return f;
@@ -117,7 +117,7 @@ struct QPoint {
 //   fv: [DOF][NV]           (NV = vc1-vc0), index i*NV+al, components relative to vc0
 // Both are pre-zeroed by the caller.
 template <int DIM, int DOF>
-__device__ inline void form_coefficients(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
+__host__ __device__ inline void form_coefficients(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
                                          int NA, int NV, double* C, double* fv) {
   (void)t;
   switch (form) {

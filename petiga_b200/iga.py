@@ -313,6 +313,9 @@ class IGA:
     def layout(self):
         return Layout(self.H.IGAGetLayout(self.h))
 
+    def SetStream(self, stream_ptr):
+        _chk(self.H.IGASetStream(self.h, C.c_void_p(stream_ptr)))
+
     def SetOption(self, name, value):
         _chk(self.H.IGASetOption(self.h, name.encode(), C.c_double(value)))
 

@@ -21,7 +21,8 @@ def dirichlet_all(dim, value=1.0, field=0):
 @pytest.mark.parametrize("path", ["quadrature", "auto"])
 def test_poisson_system(dim, p, N, path):
     case = Case(dim, p=p, N=N, bcv=dirichlet_all(dim))
-    check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL)
+    res, _ = check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL)
+    assert res["path"] == (2 if path == "auto" else 1)      # identity geometry + constant form -> separable path
 
 
 def test_poisson2d_cfg1_full_size():
