@@ -108,29 +108,43 @@ __global__ void kron_1d_kernel(DevAxis ax, const int* __restrict__ first, double
   }
 }
 
-// Which faces fix dof component c of a node with per-axis boundary codes (0 interior, 1 side 0, 2 side 1)?
-// Returns true and the value of the last face in the reference's order (d ascending, side 0 then 1).
+// Dirichlet data of a node from its per-axis boundary codes (0 interior, 1 side 0, 2 side 1): the last face in the
+// reference's order (axis ascending, side 0 then 1) wins (AddFixa overwrites, petigaelem.c:1166-1189).
 template <int DOF>
-__device__ __forceinline__ void node_fix(const KronParams& kp, const int code[3], bool fixed[DOF], double val[DOF]) {
+__device__ __forceinline__ void node_fix(const KronParams& kp, int c0, int c1, int c2, bool fixed[DOF], double val[DOF]) {
 #pragma unroll
   for (int c = 0; c < DOF; c++) { fixed[c] = false; val[c] = 0.0; }
-  for (int d = 0; d < kp.dim; d++) {
-    if (!code[d]) continue;
+  const int code[3] = {c0, c1, c2};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (d >= kp.dim || !code[d]) continue;
     const FixSide& fs = kp.bc[d][code[d] - 1];
-    for (int k = 0; k < fs.vcount; k++) { fixed[fs.vfield[k]] = true; val[fs.vfield[k]] = fs.vvalue[k]; }
+    for (int k = 0; k < fs.vcount; k++)
+#pragma unroll
+      for (int c = 0; c < DOF; c++)
+        if (fs.vfield[k] == c) { fixed[c] = true; val[c] = fs.vvalue[k]; }
   }
 }
 
+__device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return periodic ? 0 : ((col == 0) ? 1 : ((col == nnp - 1) ? 2 : 0)); }
+
+// One CTA per (A_j, A_k) pencil of owned rows; warps walk the rows A_i of the pencil; lanes walk the entries of a
+// row in storage order, so every store instruction writes 256 contiguous bytes.
 template <int DOF, bool SIMPLE>
 __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ KronParams kp) {
-  __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk]
-  __shared__ int colcode[kMaxWW];                // boundary codes of the (j,k) part of the column node: cj | ck<<2
+  __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
+  __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
+  __shared__ int jkp1[kMaxWW];
+  __shared__ double rowA[8][4][kMaxW + 1];
+  __shared__ int rowS[8][kMaxW + 1];
   const int Aj = kp.ls[1] + (int)(blockIdx.x % kp.lw[1]), Ak = kp.ls[2] + (int)(blockIdx.x / kp.lw[1]);
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
   const int Wj = kp.Wg[1][gj], Wk = kp.Wg[2][gk], Wjk = Wj * Wk;
   const int fj = kp.first[1][Aj], fk = kp.first[2][Ak];
+  const bool fixing = kp.any_bc && kp.slot == PETIGA_SLOT_SYSTEM;
   for (int t = threadIdx.x; t < 4 * DOF * DOF * kMaxWW; t += blockDim.x) (&G[0][0][0])[t] = 0.0;
   __syncthreads();
+  bool jk_boundary = false;
   for (int t = threadIdx.x; t < Wjk; t += blockDim.x) {
     const int cj = t % Wj, ck = t / Wj;
     for (int n = 0; n < kp.nterms; n++) {
@@ -139,107 +153,126 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       const double mk = kp.M[2][((size_t)tm.rs2 * kp.nnp[2] + Ak) * kMaxW + ck];
       G[tm.rs0][tm.ij][t] += tm.c * mj * mk;
     }
-    int code = 0;
-    if (!kp.periodic[1]) { int col = fj + cj; code |= (col == 0) ? 1 : ((col == kp.nnp[1] - 1) ? 2 : 0); }
-    if (!kp.periodic[2]) { int col = fk + ck; code |= ((col == 0) ? 1 : ((col == kp.nnp[2] - 1) ? 2 : 0)) << 2; }
-    colcode[t] = code;
+    int info = bcode(fj + cj, kp.nnp[1], kp.periodic[1]) | (bcode(fk + ck, kp.nnp[2], kp.periodic[2]) << 2);
+    if (cj == Aj - fj && ck == Ak - fk) info |= 16;
+    int p1 = 0;
+    if (!SIMPLE) {
+      const uint32_t s1 = kp.seg[1][gj * kMaxW + cj], s2 = kp.seg[2][gk * kMaxW + ck];
+      const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
+      const int Bk = s2 & 255, Sk = (s2 >> 8) & 255, Lk = (s2 >> 16) & 255;
+      p1 = Bk * Wj + Sk * Bj;
+      info |= (Sk * Sj) << 8;
+      info |= (Lk * Sj + Lj) << 16;
+    }
+    jkinfo[t] = info;
+    jkp1[t] = p1;
   }
+  // does any column of this pencil touch a (j,k) boundary face?  (uniform over the CTA)
+  jk_boundary = fixing && ((!kp.periodic[1] && (fj == 0 || fj + Wj == kp.nnp[1])) || (!kp.periodic[2] && (fk == 0 || fk + Wk == kp.nnp[2])));
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool want_mat = kp.values != nullptr, want_vec = kp.rhs != nullptr;
-  const bool fixing = kp.any_bc && kp.slot == PETIGA_SLOT_SYSTEM;
-  const int rcodej = kp.periodic[1] ? 0 : ((Aj == 0) ? 1 : ((Aj == kp.nnp[1] - 1) ? 2 : 0));
-  const int rcodek = kp.periodic[2] ? 0 : ((Ak == 0) ? 1 : ((Ak == kp.nnp[2] - 1) ? 2 : 0));
+  const int rcj = bcode(Aj, kp.nnp[1], kp.periodic[1]), rck = bcode(Ak, kp.nnp[2], kp.periodic[2]);
   for (int il = warp; il < kp.lw[0]; il += nwarps) {
     const int Ai = kp.ls[0] + il, gi = Ai - kp.gs[0];
     const int Wi = kp.Wg[0][gi], fi = kp.first[0][Ai], W = Wi * Wjk;
     const int lr = il + kp.lw[0] * ((Aj - kp.ls[1]) + kp.lw[1] * (Ak - kp.ls[2]));
     const int64_t base = kp.rowbase[lr];
-    int rcode[3] = {kp.periodic[0] ? 0 : ((Ai == 0) ? 1 : ((Ai == kp.nnp[0] - 1) ? 2 : 0)), rcodej, rcodek};
+    __syncwarp();
+    for (int t = lane; t < 4 * kMaxW; t += 32) {
+      const int rs = t / kMaxW, ci = t - rs * kMaxW;
+      rowA[warp][rs][ci] = (ci < Wi && ((kp.rsmask0 >> rs) & 1)) ? kp.M[0][((size_t)rs * kp.nnp[0] + Ai) * kMaxW + ci] : 0.0;
+    }
+    if (!SIMPLE && lane < Wi) rowS[warp][lane] = (int)kp.seg[0][gi * kMaxW + lane];
+    __syncwarp();
+    const int rci = bcode(Ai, kp.nnp[0], kp.periodic[0]);
+    const bool row_boundary = fixing && (rci | rcj | rck);
+    const bool col_boundary = jk_boundary || (fixing && !kp.periodic[0] && (fi == 0 || fi + Wi == kp.nnp[0]));
+    const unsigned inv = (65536u + Wi - 1) / Wi;
+    double racc[DOF];
+#pragma unroll
+    for (int c = 0; c < DOF; c++) racc[c] = 0.0;
     bool rfix[DOF];
     double rval[DOF];
 #pragma unroll
     for (int c = 0; c < DOF; c++) { rfix[c] = false; rval[c] = 0.0; }
-    if (fixing) {
-      node_fix<DOF>(kp, rcode, rfix, rval);
+    const double nelem = (double)(kp.nsup[0][Ai] * kp.nsup[1][Aj] * kp.nsup[2][Ak]);
+    if (row_boundary) {
+      node_fix<DOF>(kp, rci, rcj, rck, rfix, rval);
       if (kp.fixtable) {
         const int gidx = gi + kp.gw[0] * (gj + kp.gw[1] * gk);
 #pragma unroll
         for (int c = 0; c < DOF; c++) if (rfix[c]) rval[c] = kp.fixtable[(size_t)gidx * DOF + c];
       }
     }
-    const double nelem = (double)(kp.nsup[0][Ai] * kp.nsup[1][Aj] * kp.nsup[2][Ak]);
-    const int dci = Ai - fi, dcj = Aj - fj, dck = Ak - fk;     // column offsets of the diagonal entry
-    double racc[DOF];
+    if (want_mat || col_boundary) {
+      const bool slow = row_boundary || col_boundary;
+      for (int e = lane; e < W; e += 32) {
+        const int cjk = (int)((e * inv) >> 16), ci = e - cjk * Wi;
+        const int info = jkinfo[cjk];
+        int pos = e;
+        if (!SIMPLE) {
+          const int s0 = rowS[warp][ci];
+          const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
+          pos = jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li;
+        }
+        const double a0 = rowA[warp][0][ci], a1 = rowA[warp][1][ci], a2 = rowA[warp][2][ci], a3 = rowA[warp][3][ci];
+        double v[DOF * DOF];
 #pragma unroll
-    for (int c = 0; c < DOF; c++) racc[c] = 0.0;
-    const unsigned inv = (65536u + Wi - 1) / Wi;
-    for (int e = lane; e < W; e += 32) {
-      const int cjk = (int)((e * inv) >> 16), ci = e - cjk * Wi;
-      double a[4];
-#pragma unroll
-      for (int rs = 0; rs < 4; rs++) a[rs] = (kp.rsmask0 >> rs) & 1 ? kp.M[0][((size_t)rs * kp.nnp[0] + Ai) * kMaxW + ci] : 0.0;
-      int pos = e;
-      if (!SIMPLE) {
-        const int cj = cjk % Wj, ck = cjk / Wj;
-        const uint32_t s0 = kp.seg[0][gi * kMaxW + ci], s1 = kp.seg[1][gj * kMaxW + cj], s2 = kp.seg[2][gk * kMaxW + ck];
-        const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
-        const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
-        const int Bk = s2 & 255, Sk = (s2 >> 8) & 255, Lk = (s2 >> 16) & 255;
-        pos = Bk * Wj * Wi + Sk * (Bj * Wi + Sj * Bi) + (Lk * Sj + Lj) * Si + Li;
-      }
-      bool cfix[DOF];
-      double cval[DOF];
-#pragma unroll
-      for (int c = 0; c < DOF; c++) { cfix[c] = false; cval[c] = 0.0; }
-      bool isdiag = false;
-      if (fixing) {
-        const int cc = colcode[cjk];
-        int ccode[3] = {0, cc & 3, cc >> 2};
-        if (!kp.periodic[0]) { int col = fi + ci; ccode[0] = (col == 0) ? 1 : ((col == kp.nnp[0] - 1) ? 2 : 0); }
-        if (ccode[0] | ccode[1] | ccode[2]) {
-          node_fix<DOF>(kp, ccode, cfix, cval);
-          if (kp.fixtable) {
+        for (int ij = 0; ij < DOF * DOF; ij++) {
+          double x = a0 * G[0][ij][cjk];
+          x = fma(a3, G[3][ij][cjk], x);
+          if (DOF > 1 || (kp.rsmask0 & 6)) { x = fma(a1, G[1][ij][cjk], x); x = fma(a2, G[2][ij][cjk], x); }
+          v[ij] = x;
+        }
+        if (slow) {   // boundary rows / boundary columns only
+          bool cfix[DOF];
+          double cval[DOF];
+          const int cci = bcode(fi + ci, kp.nnp[0], kp.periodic[0]);
+          node_fix<DOF>(kp, cci, info & 3, (info >> 2) & 3, cfix, cval);
+          if (kp.fixtable && (cci | (info & 15))) {
             const int cj = cjk % Wj, ck = cjk / Wj;
-            // the column node inside this rank's ghost box (single-rank use; see kron_applicable)
             const int hi = wrapi(fi + ci, kp.nnp[0]) - kp.gs[0], hj = wrapi(fj + cj, kp.nnp[1]) - kp.gs[1], hk = wrapi(fk + ck, kp.nnp[2]) - kp.gs[2];
             const int gidx = hi + kp.gw[0] * (hj + kp.gw[1] * hk);
 #pragma unroll
             for (int c = 0; c < DOF; c++) if (cfix[c]) cval[c] = kp.fixtable[(size_t)gidx * DOF + c];
           }
+          const bool isdiag = (info & 16) && (ci == Ai - fi);
+#pragma unroll
+          for (int i = 0; i < DOF; i++)
+#pragma unroll
+            for (int j = 0; j < DOF; j++) {
+              double x = v[i * DOF + j];
+              if (rfix[i]) x = (isdiag && i == j) ? nelem : 0.0;
+              else if (cfix[j]) { racc[i] -= x * cval[j]; x = 0.0; }
+              v[i * DOF + j] = x;
+            }
         }
-        const int cj = cjk % Wj, ck = cjk / Wj;
-        isdiag = (ci == dci) && (cj == dcj) && (ck == dck);
+        if (want_mat) {
+          if (DOF == 1) kp.values[(size_t)(base + pos)] = v[0];
+          else {
+#pragma unroll
+            for (int i = 0; i < DOF; i++)
+#pragma unroll
+              for (int j = 0; j < DOF; j++) {
+                size_t off;
+                if (kp.block) off = (size_t)(base + pos) * DOF * DOF + j * DOF + i;
+                else off = (size_t)base * DOF * DOF + (size_t)i * W * DOF + (size_t)pos * DOF + j;
+                kp.values[off] = v[i * DOF + j];
+              }
+          }
+        }
       }
-#pragma unroll
-      for (int i = 0; i < DOF; i++)
-#pragma unroll
-        for (int j = 0; j < DOF; j++) {
-          const int ij = i * DOF + j;
-          double v = a[0] * G[0][ij][cjk];
-          v = fma(a[1], G[1][ij][cjk], v);
-          v = fma(a[2], G[2][ij][cjk], v);
-          v = fma(a[3], G[3][ij][cjk], v);
-          if (fixing) {
-            if (rfix[i]) v = (isdiag && i == j) ? nelem : 0.0;
-            else if (cfix[j]) { racc[i] -= v * cval[j]; v = 0.0; }
-          }
-          if (want_mat) {
-            size_t off;
-            if (DOF == 1) off = (size_t)(base + pos);
-            else if (kp.block) off = (size_t)(base + pos) * DOF * DOF + j * DOF + i;
-            else off = (size_t)base * DOF * DOF + (size_t)i * W * DOF + (size_t)pos * DOF + j;
-            kp.values[off] = v;
-          }
-        }
     }
     if (want_vec) {
+      if (col_boundary) {
 #pragma unroll
-      for (int c = 0; c < DOF; c++) {
-        double r = racc[c];
+        for (int c = 0; c < DOF; c++) {
+          double r = racc[c];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-        racc[c] = r;
+          for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+          racc[c] = r;
+        }
       }
       if (lane == 0) {
 #pragma unroll
@@ -250,8 +283,9 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
             if (vt.i != c) continue;
             F += vt.c * kp.mv[0][vt.r0 * kp.nnp[0] + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
           }
-          if (fixing) {
+          if (row_boundary) {
             // AddFlux: loads on the faces this node lies on, summed over the face elements that contain it
+            const int rcode[3] = {rci, rcj, rck};
             for (int d = 0; d < kp.dim; d++) {
               if (!rcode[d]) continue;
               const FixSide& fs = kp.bc[d][rcode[d] - 1];
@@ -264,9 +298,9 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
               }
               for (int k = 0; k < fs.lcount; k++) if (fs.lfield[k] == c) F += fs.lvalue[k] * A;
             }
-            F += racc[c];
-            if (rfix[c]) F = nelem * rval[c];
           }
+          F += racc[c];
+          if (rfix[c]) F = nelem * rval[c];
           kp.rhs[(size_t)lr * DOF + c] = F;
         }
       }
