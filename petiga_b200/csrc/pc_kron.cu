@@ -135,8 +135,6 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
-  __shared__ double rowA[8][4][kMaxW + 1];
-  __shared__ int rowS[8][kMaxW + 1];
   const int Aj = kp.ls[1] + (int)(blockIdx.x % kp.lw[1]), Ak = kp.ls[2] + (int)(blockIdx.x / kp.lw[1]);
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
   const int Wj = kp.Wg[1][gj], Wk = kp.Wg[2][gk], Wjk = Wj * Wk;
@@ -173,22 +171,62 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool want_mat = kp.values != nullptr, want_vec = kp.rhs != nullptr;
   const int rcj = bcode(Aj, kp.nnp[1], kp.periodic[1]), rck = bcode(Ak, kp.nnp[2], kp.periodic[2]);
-  for (int il = warp; il < kp.lw[0]; il += nwarps) {
-    const int Ai = kp.ls[0] + il, gi = Ai - kp.gs[0];
-    const int Wi = kp.Wg[0][gi], fi = kp.first[0][Ai], W = Wi * Wjk;
-    const int lr = il + kp.lw[0] * ((Aj - kp.ls[1]) + kp.lw[1] * (Ak - kp.ls[2]));
-    const int64_t base = kp.rowbase[lr];
-    __syncwarp();
-    for (int t = lane; t < 4 * kMaxW; t += 32) {
-      const int rs = t / kMaxW, ci = t - rs * kMaxW;
-      rowA[warp][rs][ci] = (ci < Wi && ((kp.rsmask0 >> rs) & 1)) ? kp.M[0][((size_t)rs * kp.nnp[0] + Ai) * kMaxW + ci] : 0.0;
+  // everything the row loop needs, in registers (the parameter block lives in constant memory)
+  const int lw0 = kp.lw[0], ls0 = kp.ls[0], gs0 = kp.gs[0], nnp0 = kp.nnp[0], per0 = kp.periodic[0];
+  const int* __restrict__ Wg0 = kp.Wg[0];
+  const int* __restrict__ first0 = kp.first[0];
+  const double* __restrict__ M0 = kp.M[0];
+  const int64_t* __restrict__ rowbase = kp.rowbase;
+  double* __restrict__ values = kp.values;
+  double* __restrict__ rhs = kp.rhs;
+  const int rsmask0 = kp.rsmask0;
+  const int lr0 = lw0 * ((Aj - kp.ls[1]) + kp.lw[1] * (Ak - kp.ls[2]));
+  const bool fast_ok = (DOF == 1) && SIMPLE && !(rsmask0 & 6) && want_mat;
+  // right-hand side of an unconstrained row when the load is a single separable term (Poisson, mass)
+  const bool vsimple = want_vec && DOF == 1 && kp.nvterms == 1;
+  const double vjk = vsimple ? kp.vterms[0].c * kp.mv[1][kp.vterms[0].r1 * kp.nnp[1] + Aj] * kp.mv[2][kp.vterms[0].r2 * kp.nnp[2] + Ak] : 0.0;
+  const double* __restrict__ mv0 = kp.mv[0] + (vsimple ? kp.vterms[0].r0 * nnp0 : 0);
+  for (int il = warp; il < lw0; il += nwarps) {
+    const int Ai = ls0 + il, gi = Ai - gs0;
+    const int Wi = __ldg(Wg0 + gi), fi = __ldg(first0 + Ai), W = Wi * Wjk;
+    const int lr = il + lr0;
+    const int64_t base = __ldg(rowbase + lr);
+    if (fast_ok) {
+      const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
+      const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
+      if (!rowb && !colb) {
+        // interior row: out[cjk*Wi + ci] = M00_i[ci]*G0[cjk] + M11_i[ci]*G3[cjk]; lane = (ci, group), groups stride cjk
+        const unsigned inv = (65536u + Wi - 1) / Wi;
+        const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
+        if (grp < ngrp) {
+          const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
+          double* out = values + base + grp * Wi + ci;
+          const double* g0 = &G[0][0][grp];
+          const double* g3 = &G[3][0][grp];
+          const int ostep = ngrp * Wi;
+#pragma unroll 4
+          for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+            *out = fma(a3, *g3, a0 * *g0);
+            out += ostep; g0 += ngrp; g3 += ngrp;
+          }
+        }
+        if (want_vec && lane == 0) {
+          if (vsimple) rhs[lr] = vjk * __ldg(mv0 + Ai);
+          else {
+            double F = 0.0;
+            for (int n = 0; n < kp.nvterms; n++) {
+              const KronVTerm vt = kp.vterms[n];
+              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+            }
+            rhs[lr] = F;
+          }
+        }
+        continue;
+      }
     }
-    if (!SIMPLE && lane < Wi) rowS[warp][lane] = (int)kp.seg[0][gi * kMaxW + lane];
-    __syncwarp();
     const int rci = bcode(Ai, kp.nnp[0], kp.periodic[0]);
     const bool row_boundary = fixing && (rci | rcj | rck);
     const bool col_boundary = jk_boundary || (fixing && !kp.periodic[0] && (fi == 0 || fi + Wi == kp.nnp[0]));
-    const unsigned inv = (65536u + Wi - 1) / Wi;
     double racc[DOF];
 #pragma unroll
     for (int c = 0; c < DOF; c++) racc[c] = 0.0;
@@ -206,47 +244,53 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       }
     }
     if (want_mat || col_boundary) {
+      // lane -> (fixed column offset ci along axis 0, group); a group walks cjk with stride ngrp, so one warp store
+      // covers ngrp*Wi consecutive entries of the row
+      const int ngrp = 32 / Wi, grp = lane / Wi, ci = lane - grp * Wi;
       const bool slow = row_boundary || col_boundary;
-      for (int e = lane; e < W; e += 32) {
-        const int cjk = (int)((e * inv) >> 16), ci = e - cjk * Wi;
-        const int info = jkinfo[cjk];
-        int pos = e;
-        if (!SIMPLE) {
-          const int s0 = rowS[warp][ci];
-          const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
-          pos = jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li;
-        }
-        const double a0 = rowA[warp][0][ci], a1 = rowA[warp][1][ci], a2 = rowA[warp][2][ci], a3 = rowA[warp][3][ci];
+      double a[4];
+#pragma unroll
+      for (int rs = 0; rs < 4; rs++) a[rs] = ((kp.rsmask0 >> rs) & 1) ? kp.M[0][((size_t)rs * kp.nnp[0] + Ai) * kMaxW + ci] : 0.0;
+      int Bi = 0, Si = 1, Li = ci;
+      if (!SIMPLE) { const uint32_t s0 = kp.seg[0][gi * kMaxW + ci]; Bi = s0 & 255; Si = (s0 >> 8) & 255; Li = (s0 >> 16) & 255; }
+      const int cci = slow ? bcode(fi + ci, kp.nnp[0], kp.periodic[0]) : 0;
+      const bool diag_i = (ci == Ai - fi);
+      const bool rs12 = (DOF > 1) || (kp.rsmask0 & 6);
+      for (int cjk = (grp < ngrp) ? grp : Wjk; cjk < Wjk; cjk += ngrp) {
         double v[DOF * DOF];
 #pragma unroll
         for (int ij = 0; ij < DOF * DOF; ij++) {
-          double x = a0 * G[0][ij][cjk];
-          x = fma(a3, G[3][ij][cjk], x);
-          if (DOF > 1 || (kp.rsmask0 & 6)) { x = fma(a1, G[1][ij][cjk], x); x = fma(a2, G[2][ij][cjk], x); }
+          double x = a[0] * G[0][ij][cjk];
+          x = fma(a[3], G[3][ij][cjk], x);
+          if (rs12) { x = fma(a[1], G[1][ij][cjk], x); x = fma(a[2], G[2][ij][cjk], x); }
           v[ij] = x;
         }
-        if (slow) {   // boundary rows / boundary columns only
-          bool cfix[DOF];
-          double cval[DOF];
-          const int cci = bcode(fi + ci, kp.nnp[0], kp.periodic[0]);
-          node_fix<DOF>(kp, cci, info & 3, (info >> 2) & 3, cfix, cval);
-          if (kp.fixtable && (cci | (info & 15))) {
-            const int cj = cjk % Wj, ck = cjk / Wj;
-            const int hi = wrapi(fi + ci, kp.nnp[0]) - kp.gs[0], hj = wrapi(fj + cj, kp.nnp[1]) - kp.gs[1], hk = wrapi(fk + ck, kp.nnp[2]) - kp.gs[2];
-            const int gidx = hi + kp.gw[0] * (hj + kp.gw[1] * hk);
+        int pos = cjk * Wi + ci;
+        if (!SIMPLE || slow) {
+          const int info = jkinfo[cjk];
+          if (!SIMPLE) pos = jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li;
+          if (slow) {   // boundary rows / boundary columns only
+            bool cfix[DOF];
+            double cval[DOF];
+            node_fix<DOF>(kp, cci, info & 3, (info >> 2) & 3, cfix, cval);
+            if (kp.fixtable && (cci | (info & 15))) {
+              const int cj = cjk % Wj, ck = cjk / Wj;
+              const int hi = wrapi(fi + ci, kp.nnp[0]) - kp.gs[0], hj = wrapi(fj + cj, kp.nnp[1]) - kp.gs[1], hk = wrapi(fk + ck, kp.nnp[2]) - kp.gs[2];
+              const int gidx = hi + kp.gw[0] * (hj + kp.gw[1] * hk);
 #pragma unroll
-            for (int c = 0; c < DOF; c++) if (cfix[c]) cval[c] = kp.fixtable[(size_t)gidx * DOF + c];
-          }
-          const bool isdiag = (info & 16) && (ci == Ai - fi);
-#pragma unroll
-          for (int i = 0; i < DOF; i++)
-#pragma unroll
-            for (int j = 0; j < DOF; j++) {
-              double x = v[i * DOF + j];
-              if (rfix[i]) x = (isdiag && i == j) ? nelem : 0.0;
-              else if (cfix[j]) { racc[i] -= x * cval[j]; x = 0.0; }
-              v[i * DOF + j] = x;
+              for (int c = 0; c < DOF; c++) if (cfix[c]) cval[c] = kp.fixtable[(size_t)gidx * DOF + c];
             }
+            const bool isdiag = (info & 16) && diag_i;
+#pragma unroll
+            for (int i = 0; i < DOF; i++)
+#pragma unroll
+              for (int j = 0; j < DOF; j++) {
+                double x = v[i * DOF + j];
+                if (rfix[i]) x = (isdiag && i == j) ? nelem : 0.0;
+                else if (cfix[j]) { racc[i] -= x * cval[j]; x = 0.0; }
+                v[i * DOF + j] = x;
+              }
+          }
         }
         if (want_mat) {
           if (DOF == 1) kp.values[(size_t)(base + pos)] = v[0];
