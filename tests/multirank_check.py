@@ -1,0 +1,95 @@
+"""Multi-rank parity check, run under torchrun (one rank per GPU):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multirank_check.py
+Every rank assembles its part on its GPU (ghost rows exchanged over NCCL, state halo over NCCL) and compares its
+owned rows with the oracle's global assembly emulating the same number of ranks."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import petiga_b200 as pb
+    from tests.common import Case, oracle_to_layout, rel_frobenius, state_vectors
+    from tests.gpu_common import run_product, MAT_SLOTS, VEC_SLOTS
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = pb.load_cuda()
+    idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = (C.c_ubyte * 128)()
+        assert L.petiga_cuda_comm_unique_id(raw) == 0
+        idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+    dist.broadcast(idbuf, 0)
+    raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+    comm = C.c_void_p()
+    assert L.petiga_cuda_comm_init(C.byref(comm), world, rank, raw, local) == 0, L.petiga_cuda_last_error()
+
+    dall = lambda dim, v=1.0: [(d, s, 0, v) for d in range(dim) for s in range(2)]
+    cases = [
+        ("poisson3d p2", Case(3, p=2, N=8, bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("poisson3d p3", Case(3, p=3, N=(9, 8, 10), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("poisson2d p2", Case(2, p=2, N=(16, 12), bcv=dall(2, 0.5)), "SYSTEM", "POISSON", [], False),
+        ("elasticity3d", Case(3, dof=3, p=2, N=6, bcv=[(0, 0, 0, 0.0), (0, 0, 1, 0.0), (0, 0, 2, 0.0), (0, 1, 0, 1.0)]), "SYSTEM", "ELASTICITY3D", [1.0, 1.0], False),
+        ("elasticity3d aij", Case(3, dof=3, p=2, N=6, mattype="aij", bcv=[(0, 0, 0, 0.0), (0, 1, 0, 1.0)]), "SYSTEM", "ELASTICITY3D", [1.0, 1.0], False),
+        ("mass periodic dof2", Case(2, dof=2, p=2, N=(24, 20), periodic=(True, False)), "SYSTEM", "MASS", [], False),
+        ("mapped poisson", Case(3, p=2, N=8, geometry=("perturbed", 0.05), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("cahnhilliard IJ", Case(2, p=2, N=32, C=1, periodic=True), "IJACOBIAN", "CAHNHILLIARD2D", [1.5, 3000.0], True),
+        ("cahnhilliard IF", Case(2, p=2, N=32, C=1, periodic=True), "IFUNCTION", "CAHNHILLIARD2D", [1.5, 3000.0], True),
+        ("bratu F", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "FUNCTION", "BRATU", [6.8], True),
+        ("bratu J", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "JACOBIAN", "BRATU", [6.8], True),
+    ]
+    nfail = 0
+    for name, case, slot, form, prm, state in cases:
+        o = case.oracle()
+        o.setup()
+        rp, ci, rs = o.pattern(world)
+        n = len(rp) - 1
+        U = V = None
+        if state:
+            U, V = state_vectors(n * case.dof)
+        Ko, Fo = o.assemble(slot, form, prm, size=world, shift=7.0, V=V, U=U)
+        r0, r1 = int(rs[rank]), int(rs[rank + 1])
+        for path in (["quadrature", "auto"] if not state else ["quadrature"]):
+            g = case.product(rank=rank, size=world, nccl=comm.value, device=local)
+            Ul = None if U is None else U[r0 * case.dof:r1 * case.dof]
+            Vl = None if V is None else V[r0 * case.dof:r1 * case.dof]
+            res = run_product(case, slot, form, prm, U=Ul, V=Vl if slot in ("IFUNCTION", "IJACOBIAN") else None, shift=7.0, path=path, g=g)
+            ok, msg = True, ""
+            if slot in MAT_SLOTS:
+                rpl = rp[r0:r1 + 1] - rp[r0]
+                cil = ci[rp[r0]:rp[r1]]
+                if res["baij"] or case.dof == 1:
+                    ok &= bool(np.array_equal(res["rowptr"], rpl) and np.array_equal(res["colidx"], cil))
+                exp = oracle_to_layout(Ko[rp[r0]:rp[r1]], rpl, case.dof, res["baij"])
+                e = rel_frobenius(res["values"], exp)
+                ok &= e <= 1e-12
+                msg += " K=%.1e" % e
+            if slot in VEC_SLOTS:
+                e = rel_frobenius(res["rhs"], Fo[r0:r1].reshape(-1))
+                ok &= e <= 1e-12
+                msg += " F=%.1e" % e
+            flag = torch.tensor([0 if ok else 1], device="cuda")
+            dist.all_reduce(flag)
+            if rank == 0:
+                print("%-20s %-10s path=%d %s%s" % (name, path, res["path"], "ok " if flag.item() == 0 else "FAIL", msg), flush=True)
+            nfail += int(flag.item() != 0)
+            g.Destroy()
+    dist.barrier()
+    if rank == 0:
+        print("MULTIRANK %s: %d failures on %d ranks" % ("PASS" if nfail == 0 else "FAIL", nfail, world), flush=True)
+    L.petiga_cuda_comm_destroy(comm)
+    dist.destroy_process_group()
+    return 1 if nfail else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -225,3 +225,21 @@ def test_cfg2_full_size_properties():
     v = row_values(idx(0, 64, 64))
     assert np.count_nonzero(v) == 1 and v.sum() == 16.0
     A.destroy(); B.destroy()
+
+
+# ---- multi-GPU: ghost-row exchange + state halo over NCCL (skipped on a single-GPU box) ------------------------
+def test_multirank_nccl_parity():
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "multirank_check.py")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    print(out.stdout[-4000:])
+    assert "MULTIRANK PASS" in out.stdout
