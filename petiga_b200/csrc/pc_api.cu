@@ -139,7 +139,7 @@ int petiga_cuda_plan_create(petiga_cuda_plan** plan, const petiga_cuda_space* sp
     DevAxis& da = P->dax[d];
     const size_t nq = (size_t)a.nel * a.nqp;
     if (!sp->value[d] || !sp->weight[d] || !sp->point[d] || !sp->detJac[d]) { set_error("missing basis tables"); return bail(PETIGA_CUDA_ERR_ARG); }
-    double *v, *w, *pt, *dj; int *off, *W, *lo; uint32_t* seg;
+    double *v, *w, *pt, *dj; int *off, *W, *lo, *simp; uint32_t* seg;
     if ((rc = upload(P, sp->value[d], nq * (a.p + 1) * 5, &v))) return bail(rc);
     if ((rc = upload(P, sp->weight[d], nq, &w))) return bail(rc);
     if ((rc = upload(P, sp->point[d], nq, &pt))) return bail(rc);
@@ -148,7 +148,8 @@ int petiga_cuda_plan_create(petiga_cuda_plan** plan, const petiga_cuda_space* sp
     if ((rc = upload(P, a.W.data(), a.W.size(), &W))) return bail(rc);
     if ((rc = upload(P, a.lo.data(), a.lo.size(), &lo))) return bail(rc);
     if ((rc = upload(P, a.seg.data(), a.seg.size(), &seg))) return bail(rc);
-    da.value = v; da.weight = w; da.point = pt; da.detJac = dj; da.offset = off; da.W = W; da.lo = lo; da.seg = seg;
+    if ((rc = upload(P, a.simple.data(), a.simple.size(), &simp))) return bail(rc);
+    da.value = v; da.weight = w; da.point = pt; da.detJac = dj; da.offset = off; da.W = W; da.lo = lo; da.seg = seg; da.simple = simp;
     da.nel = a.nel; da.nqp = a.nqp; da.nen = a.p + 1; da.p = a.p; da.gs = a.gs; da.gw = a.gw; da.es = a.es; da.ew = a.ew;
     da.periodic = a.periodic; da.nnp = a.nnp;
     P->detJac_h[d].assign(sp->detJac[d], sp->detJac[d] + a.nel);

@@ -18,6 +18,7 @@ struct DevAxis {
   const int* W;           // [gw]  1-D row width by ghost coordinate
   const int* lo;          // [gw]  row coordinate - first column
   const uint32_t* seg;    // [gw][kMaxW] packed (B | S<<8 | L<<16)
+  const int* simple;      // [gw]  1: columns of this row are already in storage order
   int nel, nqp, nen, p, gs, gw, es, ew, periodic, nnp;
 };
 

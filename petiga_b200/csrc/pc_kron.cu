@@ -40,6 +40,7 @@ struct KronParams {
   const int* Wg[3];       // [gw] widths by ghost coordinate
   const int* lo[3];       // [gw]
   const uint32_t* seg[3]; // [gw][kMaxW]
+  const int* simp[3];     // [gw] columns of this 1-D row are already in storage order
   int ls[3], lw[3], gs[3], nnp[3], periodic[3];
   const int64_t* rowbase;
   const int* localrow;    // ghost box -> local row (for the fix table)
@@ -130,7 +131,7 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 
 // One CTA per (A_j, A_k) pencil of owned rows; warps walk the rows A_i of the pencil; lanes walk the entries of a
 // row in storage order, so every store instruction writes 256 contiguous bytes.
-template <int DOF, bool SIMPLE>
+template <int DOF>
 __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ KronParams kp) {
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
     int info = bcode(fj + cj, kp.nnp[1], kp.periodic[1]) | (bcode(fk + ck, kp.nnp[2], kp.periodic[2]) << 2);
     if (cj == Aj - fj && ck == Ak - fk) info |= 16;
     int p1 = 0;
-    if (!SIMPLE) {
+    {
       const uint32_t s1 = kp.seg[1][gj * kMaxW + cj], s2 = kp.seg[2][gk * kMaxW + ck];
       const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
       const int Bk = s2 & 255, Sk = (s2 >> 8) & 255, Lk = (s2 >> 16) & 255;
@@ -181,7 +182,9 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   double* __restrict__ rhs = kp.rhs;
   const int rsmask0 = kp.rsmask0;
   const int lr0 = lw0 * ((Aj - kp.ls[1]) + kp.lw[1] * (Ak - kp.ls[2]));
-  const bool fast_ok = (DOF == 1) && SIMPLE && !(rsmask0 & 6) && want_mat;
+  const bool simple_jk = kp.simp[1][gj] && kp.simp[2][gk];
+  const int* __restrict__ simple0 = kp.simp[0];
+  const bool fast_ok = (DOF == 1) && simple_jk && !(rsmask0 & 6) && want_mat;
   // right-hand side of an unconstrained row when the load is a single separable term (Poisson, mass)
   const bool vsimple = want_vec && DOF == 1 && kp.nvterms == 1;
   const double vjk = vsimple ? kp.vterms[0].c * kp.mv[1][kp.vterms[0].r1 * kp.nnp[1] + Aj] * kp.mv[2][kp.vterms[0].r2 * kp.nnp[2] + Ak] : 0.0;
@@ -191,7 +194,8 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
     const int Wi = __ldg(Wg0 + gi), fi = __ldg(first0 + Ai), W = Wi * Wjk;
     const int lr = il + lr0;
     const int64_t base = __ldg(rowbase + lr);
-    if (fast_ok) {
+    const bool SIMPLE = simple_jk && __ldg(simple0 + gi);
+    if (fast_ok && SIMPLE) {
       const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
       if (!rowb && !colb) {
@@ -428,7 +432,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
     const int nnp = L.ax[d].nnp;
     const size_t nM = (size_t)4 * nnp * kMaxW, nmv = (size_t)2 * nnp;
     kp.M[d] = P->d_kronrow[d]; kp.mv[d] = kp.M[d] + nM; kp.lsum[d] = kp.mv[d] + nmv; kp.nsup[d] = (const int*)(kp.lsum[d] + nnp);
-    kp.first[d] = P->d_first[d]; kp.Wg[d] = P->dax[d].W; kp.lo[d] = P->dax[d].lo; kp.seg[d] = P->dax[d].seg;
+    kp.first[d] = P->d_first[d]; kp.Wg[d] = P->dax[d].W; kp.lo[d] = P->dax[d].lo; kp.seg[d] = P->dax[d].seg; kp.simp[d] = P->dax[d].simple;
     kp.ls[d] = L.ax[d].ls; kp.lw[d] = L.ax[d].lw; kp.gs[d] = L.ax[d].gs; kp.gw[d] = L.ax[d].gw; kp.nnp[d] = nnp; kp.periodic[d] = L.ax[d].periodic;
     if (L.ax[d].periodic) simple = false;
   }
@@ -460,8 +464,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
   const int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
 #define KL(DOF_)                                                                              \
   if (L.dof == DOF_) {                                                                        \
-    if (simple) kron_rows_kernel<DOF_, true><<<blocks, threads, 0, P->stream>>>(kp);          \
-    else kron_rows_kernel<DOF_, false><<<blocks, threads, 0, P->stream>>>(kp);                \
+    kron_rows_kernel<DOF_><<<blocks, threads, 0, P->stream>>>(kp);                            \
   }
   KL(1) KL(2) KL(3)
 #undef KL

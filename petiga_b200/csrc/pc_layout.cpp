@@ -93,7 +93,7 @@ int build_layout(const petiga_cuda_space& sp, int rank, int nranks, Layout& L) {
         a.gs != sp.node_gstart[d] || a.gw != sp.node_gwidth[d])
       return fail(L, PETIGA_CUDA_ERR_ARG, "boxes in petiga_cuda_space disagree with IGA_Distribute arithmetic");
     if (a.lw < 1) return fail(L, PETIGA_CUDA_ERR_SUP, "a rank owns no nodes along an axis");
-    a.wrapped.resize(a.gw); a.W.resize(a.gw); a.lo.resize(a.gw); a.seg.assign((size_t)a.gw * kMaxW, 0);
+    a.wrapped.resize(a.gw); a.W.resize(a.gw); a.lo.resize(a.gw); a.simple.assign(a.gw, 1); a.seg.assign((size_t)a.gw * kMaxW, 0);
     for (int g = 0; g < a.gw; g++) {
       int w = wrap(a.gs + g, a.nnp);
       a.wrapped[g] = w;
@@ -116,6 +116,7 @@ int build_layout(const petiga_cuda_space& sp, int rank, int nranks, Layout& L) {
           if (key_own[e] == key_own[c]) { S++; if (key_idx[e] < key_idx[c]) Lc++; }
         }
         a.seg[(size_t)g * kMaxW + c] = (uint32_t)B | ((uint32_t)S << 8) | ((uint32_t)Lc << 16);
+        if (B != 0 || S != W || Lc != c) a.simple[g] = 0;
       }
     }
   }

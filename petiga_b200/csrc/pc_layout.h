@@ -31,6 +31,7 @@ struct AxisLayout {
   // indexed by ghost coordinate g in [0, gw):
   std::vector<int> wrapped;               // node index after periodic wrap
   std::vector<int> W, lo;                 // row width; lo = (unwrapped row coordinate) - first
+  std::vector<int> simple;                // 1 when the row's columns are already in storage order (one owner, no wrap)
   std::vector<uint32_t> seg;              // [gw][kMaxW]: B | S<<8 | L<<16 for column offset c (see below)
 };
 
