@@ -199,6 +199,7 @@ int petiga_cuda_set_option(petiga_cuda_plan* P, const char* name, double value) 
   if (!P || !name) return PETIGA_CUDA_ERR_ARG;
   if (!strcmp(name, "path")) { int v = (int)value; if (v < 0 || v > 2) return PETIGA_CUDA_ERR_ARG; P->path = v; return 0; }
   if (!strcmp(name, "scatter")) { P->scatter = (int)value; return 0; }
+  if (!strcmp(name, "quad_impl")) { P->quad_impl = (int)value; return 0; }
   set_error(std::string("unknown option ") + name);
   return PETIGA_CUDA_ERR_ARG;
 }
@@ -436,7 +437,7 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   kp.c0 = c0; kp.c1 = c1;
   memcpy(kp.prm, P->slots[slot].prm, sizeof(kp.prm));
   kp.shift = shift; kp.t = t;
-  int rc = launch_quadrature(P, kp);
+  int rc = P->quad_impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
   if (rc) return rc;
   cudaEventRecord(P->ev1, P->stream);
   if (multi) {

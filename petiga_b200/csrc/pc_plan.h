@@ -62,6 +62,7 @@ struct petiga_cuda_plan {
   struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
   int path = PETIGA_PATH_AUTO;
   int scatter = 0;
+  int quad_impl = 0;              // 0 = sum-factorised kernel (default), 1 = pair-loop kernel
   // stats
   long launches = 0;
   int last_path = 0;
@@ -80,7 +81,8 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // quadrature path (pc_quad.cu)
-int launch_quadrature(petiga_cuda_plan* P, const KParams& base);
+int launch_quadrature(petiga_cuda_plan* P, const KParams& base);      // v1: pair loop as one register-tiled contraction
+int launch_quadrature_sf(petiga_cuda_plan* P, const KParams& base);   // v2: sum-factorised
 // separable path (pc_kron.cu)
 bool kron_applicable(const petiga_cuda_plan* P, int slot, int form);
 int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, double* rhs);

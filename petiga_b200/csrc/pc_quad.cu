@@ -1,5 +1,7 @@
 // pc_quad.cu -- instantiation table and launcher of the per-element quadrature kernel.
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 #include "pc_plan.h"
 #include "pc_quad.cuh"
@@ -61,5 +63,6 @@ int launch_quadrature(petiga_cuda_plan* Pl, const KParams& base) {
   set_error("quadrature kernel: (dim, degree, dof) combination not instantiated");
   return PETIGA_CUDA_ERR_SUP;
 }
+
 
 }  // namespace pc

@@ -27,6 +27,10 @@ struct QCfg {
   static constexpr int TN = TM * DOF;
   static constexpr int GM = M / TM, GN = N / TN, G = GM * GN;
   static_assert(M % TM == 0 && N % TN == 0, "tile must divide the element matrix");
+  // Columns of a thread's tile are interleaved across the GN threads of a tile row in chunks of CH doubles, so that the
+  // threads of a warp read consecutive 8/16-byte words of the B operand (no shared-memory bank conflicts).
+  static constexpr int CH = (TN % 2 == 0) ? 2 : 1;
+  __host__ __device__ static constexpr int col(int tx, int j) { return ((j / CH) * GN + tx) * CH + (j % CH); }
 };
 
 // shared-memory carve-up of one element slot (offsets in doubles); identical on host and device
@@ -179,7 +183,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
 
   // register tile of K_e: rows a in [row0,row0+TM), columns n=(b,j,i) in [col0,col0+TN)
   const int ty = lt / GN, tx = lt - ty * GN;
-  const int row0 = ty * TM, col0 = tx * TN;
+  const int row0 = ty * TM;
   double acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; i++)
@@ -356,17 +360,27 @@ quad_kernel(const __grid_constant__ KParams prm) {
     }
     __syncthreads();
     if (valid) {
-      // B operand: T[(q,al)][(b,j,i)] = JW_q * sum_be C_q[i][j][al][be] * Psi_be(b,q)
-      if (want_mat)
-        for (int t = lt; t < nq * NA * N; t += G) {
-          int ql = t / (NA * N), r = t - ql * NA * N, al = r / N, n = r - al * N;
-          int b = n / (DOF * DOF), j = (n / DOF) % DOF, i = n % DOF;
-          const double* C = Cq + ((size_t)(prm.per_qp ? ql : 0) * DOF * DOF + i * DOF + j) * NA * NA + al * NA;
-          const double* ps = Psi + ((size_t)ql * NC + prm.mc0 - prm.c0) * M + b;
-          double s = 0.0;
-          for (int be = 0; be < NA; be++) s += C[be] * ps[be * M];
-          Bs[(size_t)(ql * NA + al) * N + n] = s * JW[ql];
+      // B operand: T[(q,al)][(b,j,i)] = JW_q * sum_be C_q[i][j][al][be] * Psi_be(b,q); a thread keeps its column n
+      if (want_mat) {
+        constexpr int PARTS = (G >= N) ? G / N : 1;
+        for (int t = lt; t < PARTS * N; t += G) {
+          const int n = t % N, part = t / N;
+          const int b = n / (DOF * DOF), j = (n / DOF) % DOF, i = n % DOF;
+          const double* Cij = Cq + (size_t)(i * DOF + j) * NA * NA;
+          const double* psb = Psi + (size_t)(prm.mc0 - prm.c0) * M + b;
+          for (int ql = part; ql < nq; ql += PARTS) {
+            const double* C = Cij + (prm.per_qp ? (size_t)ql * DOF * DOF * NA * NA : 0);
+            const double* ps = psb + (size_t)ql * NC * M;
+            const double jw = JW[ql];
+            double* out = Bs + (size_t)ql * NA * N + n;
+            for (int al = 0; al < NA; al++) {
+              double sacc = 0.0;
+              for (int be = 0; be < NA; be++) sacc += C[al * NA + be] * ps[be * M];
+              out[al * N] = sacc * jw;
+            }
+          }
         }
+      }
       // element vector: F_e[a,i] += sum_q JW_q sum_al Psi_al(a,q) f_q[i][al]
       if (want_vec && NV > 0)
         for (int t = lt; t < M * DOF; t += G) {
@@ -387,13 +401,13 @@ quad_kernel(const __grid_constant__ KParams prm) {
     if (valid && want_mat) {
       for (int ql = 0; ql < nq; ql++) {
         const double* pa = Psi + ((size_t)ql * NC + prm.mc0 - prm.c0) * M + row0;
-        const double* pb = Bs + (size_t)ql * NA * N + col0;
+        const double* pb = Bs + (size_t)ql * NA * N;
         for (int al = 0; al < NA; al++) {
           double af[TM], bf[TN];
 #pragma unroll
           for (int i = 0; i < TM; i++) af[i] = pa[al * M + i];
 #pragma unroll
-          for (int j = 0; j < TN; j++) bf[j] = pb[al * N + j];
+          for (int j = 0; j < TN; j++) bf[j] = pb[al * N + Cfg::col(tx, j)];
 #pragma unroll
           for (int i = 0; i < TM; i++)
 #pragma unroll
@@ -411,7 +425,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
     for (int i = 0; i < TM; i++)
 #pragma unroll
       for (int j = 0; j < TN; j++) {
-        int a = row0 + i, n = col0 + j;
+        int a = row0 + i, n = Cfg::col(tx, j);
         int b = n / (DOF * DOF), jj = (n / DOF) % DOF, ii = n % DOF;
         int ra = a * DOF + ii, cb = b * DOF + jj;
         bool fr = fixflag[ra], fc = fixflag[cb];
@@ -446,7 +460,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
       for (int j = 0; j < TN; j++) {
         const double v = acc[i][j];
         if (v == 0.0) continue;   // adding an exact zero cannot change the sum
-        const int n = col0 + j;
+        const int n = Cfg::col(tx, j);
         const int b = n / (DOF * DOF), jj = (n / DOF) % DOF, ii = n % DOF;
         const int ib = b % NEN1, jb = (DIM > 1) ? (b / NEN1) % NEN1 : 0, kb = (DIM > 2) ? b / (NEN1 * NEN1) : 0;
         const uint32_t s0 = segs[ia * NEN1 + ib], s1 = segs[NEN1 * NEN1 + ja * NEN1 + jb], s2 = segs[2 * NEN1 * NEN1 + ka * NEN1 + kb];
