@@ -33,6 +33,7 @@ struct petiga_cuda_plan {
   // 1-D element matrices for the separable path: [comp pair][nel][nen][nen]
   double* d_kron1d[3] = {nullptr, nullptr, nullptr};
   double* d_kronrow[3] = {nullptr, nullptr, nullptr};   // 1-D global banded matrices [4][nnp][kMaxW]
+  double* d_sfpp[3] = {nullptr, nullptr, nullptr};      // pair-product tables of the sum-factorised kernel
 
   // pattern (owned by the plan), per block mode
   int* d_rowptr[2] = {nullptr, nullptr};

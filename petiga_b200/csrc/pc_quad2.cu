@@ -13,7 +13,7 @@ namespace pc {
 namespace {
 
 template <int DIM, int DOF>
-void host_matrix_pattern(int form, int slot, const double* prm, const FormInfo& fi, std::vector<char>& pat, int& ijmask) {
+void host_matrix_pattern(int form, int slot, const double* prm, const FormInfo& fi, std::vector<char>& pat, int& ijmask, std::vector<double>& Cout) {
   const int NA = fi.mc1 - fi.mc0;
   pat.assign((size_t)std::max(NA * NA, 1), 0);
   ijmask = 0;
@@ -23,7 +23,8 @@ void host_matrix_pattern(int form, int slot, const double* prm, const FormInfo& 
     ijmask = (1 << (DOF * DOF)) - 1;
     return;
   }
-  std::vector<double> C((size_t)DOF * DOF * NA * NA, 0.0);
+  std::vector<double>& C = Cout;
+  C.assign((size_t)DOF * DOF * NA * NA, 0.0);
   QPoint q;
   memset(&q, 0, sizeof(q));
   form_coefficients<DIM, DOF>(form, slot, prm, 0.0, 0.0, q, NA, 0, C.data(), nullptr);
@@ -82,6 +83,18 @@ int build_sf_lists(const KParams& kp, const FormInfo& fi, bool mapped, bool rati
       l.pair_s[l.npairs] = (unsigned char)s; l.pair_t[l.npairs] = (unsigned char)t; l.pair_g1[l.npairs] = (unsigned char)g1;
       l.npairs++;
     }
+  {  // order the g1 groups by their g2 group so that stage B walks a contiguous range per g2
+    int perm[kMaxPairs], inv[kMaxPairs], n = 0;
+    for (int g2 = 0; g2 < l.ng2; g2++) {
+      l.g2_first[g2] = (unsigned char)n;
+      for (int g1 = 0; g1 < l.ng1; g1++) if (l.g1_g2[g1] == g2) perm[n++] = g1;
+    }
+    l.g2_first[l.ng2] = (unsigned char)n;
+    unsigned char oo1[kMaxPairs], gg2[kMaxPairs];
+    for (int k = 0; k < n; k++) { oo1[k] = l.g1_oo1[perm[k]]; gg2[k] = l.g1_g2[perm[k]]; inv[perm[k]] = k; }
+    for (int k = 0; k < n; k++) { l.g1_oo1[k] = oo1[k]; l.g1_g2[k] = gg2[k]; }
+    for (int k = 0; k < l.npairs; k++) l.pair_g1[k] = (unsigned char)inv[l.pair_g1[k]];
+  }
   l.ijmask = ijmask;
   // fields and evaluation combos
   for (int f = 0; f < 16; f++) for (int t = 0; t < kMaxT; t++) l.ev_index[f][t] = -1;
@@ -116,19 +129,10 @@ int build_sf_lists(const KParams& kp, const FormInfo& fi, bool mapped, bool rati
   return 0;
 }
 
-template <int DIM, int P, int DOF>
-int launch_sf(petiga_cuda_plan* Pl, const KParams& base, const FormInfo& fi) {
+template <int DIM, int P, int DOF, int NQ>
+int launch_sf_nq(petiga_cuda_plan* Pl, SFParams& sp) {
   using Cfg = SFCfg<DIM, P, DOF>;
-  SFParams sp;
-  sp.k = base;
-  const bool mapped = base.X != nullptr, rational = base.Wt != nullptr;
-  const bool state = base.needs_state && base.U != nullptr;
-  const bool transient = (base.slot == PETIGA_SLOT_IFUNCTION || base.slot == PETIGA_SLOT_IJACOBIAN);
-  std::vector<char> cpat;
-  int ijmask = 0;
-  host_matrix_pattern<DIM, DOF>(base.form, base.slot, base.prm, fi, cpat, ijmask);
-  int rc = build_sf_lists(base, fi, mapped, rational, state, transient, cpat, ijmask, sp.l);
-  if (rc) { set_error("sum-factorised kernel: too many components for this form"); return rc; }
+  const KParams& base = sp.k;
   const int NA = base.mc1 - base.mc0, NV = base.vc1 - base.vc0;
   const int nq[3] = {base.ax[0].nqp, base.ax[1].nqp, base.ax[2].nqp};
   const SFSmem lay(Cfg::n0, Cfg::n1, Cfg::n2, nq[0], nq[1], nq[2], DIM, DOF, sp.l, NA, NV, base.per_qp, base.c1 - base.c0);
@@ -139,7 +143,7 @@ int launch_sf(petiga_cuda_plan* Pl, const KParams& base, const FormInfo& fi) {
   sp.k.epb = epb;
   const size_t smem = per * epb;
   const int threads = ((Cfg::G * epb + 31) / 32) * 32;
-  auto kern = quad_sf_kernel<DIM, P, DOF>;
+  auto kern = quad_sf_kernel<DIM, P, DOF, NQ>;
   PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (base.nelem + epb - 1) / epb;
   if (blocks > 0) {
@@ -148,6 +152,59 @@ int launch_sf(petiga_cuda_plan* Pl, const KParams& base, const FormInfo& fi) {
     Pl->launches++;
   }
   return 0;
+}
+
+template <int DIM, int P, int DOF>
+int launch_sf(petiga_cuda_plan* Pl, const KParams& base, const FormInfo& fi) {
+  SFParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.k = base;
+  const bool mapped = base.X != nullptr, rational = base.Wt != nullptr;
+  const bool state = base.needs_state && base.U != nullptr;
+  const bool transient = (base.slot == PETIGA_SLOT_IFUNCTION || base.slot == PETIGA_SLOT_IJACOBIAN);
+  std::vector<char> cpat;
+  std::vector<double> Cc;
+  int ijmask = 0;
+  host_matrix_pattern<DIM, DOF>(base.form, base.slot, base.prm, fi, cpat, ijmask, Cc);
+  int rc = build_sf_lists(base, fi, mapped, rational, state, transient, cpat, ijmask, sp.l);
+  if (rc) { set_error("sum-factorised kernel: too many components for this form"); return rc; }
+  // per-axis pair-product tables, built once per plan
+  for (int d = 0; d < 3; d++) {
+    if (!Pl->d_sfpp[d]) {
+      const size_t n = (size_t)base.ax[d].nel * 9 * base.ax[d].nqp * base.ax[d].nen * base.ax[d].nen;
+      void* buf = nullptr;
+      PC_CUDA(cudaMalloc(&buf, n * sizeof(double)));
+      Pl->allocs.push_back(buf);
+      Pl->d_sfpp[d] = (double*)buf;
+      sf_pp_kernel<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, Pl->stream>>>(base.ax[d], Pl->d_sfpp[d]);
+      PC_CUDA(cudaGetLastError());
+      Pl->launches++;
+    }
+    sp.pp[d] = Pl->d_sfpp[d];
+  }
+  // identity geometry + constant coefficients: D'[ij][pair] is a constant times JW
+  const int NA = base.mc1 - base.mc0;
+  sp.const_dp = 0;
+  if (!mapped && !rational && !fi.per_qp && NA > 0 && DOF * DOF <= 9) {
+    sp.const_dp = 1;
+    auto phys_of = [&](int t) -> int {   // tensor component -> physical component (identity map)
+      if (t == sp.l.tN) return 0;
+      for (int d = 0; d < DIM; d++) if (t == sp.l.tG[d]) return 1 + d;
+      return DIM + 1;
+    };
+    for (int ij = 0; ij < DOF * DOF; ij++)
+      for (int pr = 0; pr < sp.l.npairs; pr++) {
+        const int al = phys_of(sp.l.pair_s[pr]) - base.mc0, be = phys_of(sp.l.pair_t[pr]) - base.mc0;
+        double c = 0.0;
+        if (al >= 0 && al < NA && be >= 0 && be < NA) c = Cc[((size_t)ij * NA + al) * NA + be];
+        sp.cconst[ij * kMaxPairs + pr] = c;
+      }
+  }
+  const int nq0 = base.ax[0].nqp;
+  bool def = (nq0 == P + 1);
+  for (int d = 1; d < DIM; d++) def = def && base.ax[d].nqp == P + 1;
+  if (def) return launch_sf_nq<DIM, P, DOF, P + 1>(Pl, sp);
+  return launch_sf_nq<DIM, P, DOF, 0>(Pl, sp);
 }
 
 }  // namespace

@@ -30,7 +30,7 @@ struct SFLists {
   int torder[kMaxT][3];
   int npairs; unsigned char pair_s[kMaxPairs], pair_t[kMaxPairs], pair_g1[kMaxPairs];
   int ng1; unsigned char g1_oo1[kMaxPairs], g1_g2[kMaxPairs];
-  int ng2; unsigned char g2_oo2[9];
+  int ng2; unsigned char g2_oo2[9]; unsigned char g2_first[10];   // g1 groups of g2 are [g2_first[g2], g2_first[g2+1])
   int nev; unsigned char ev_field[kMaxEval], ev_t[kMaxEval];   // evaluation combos (field, tensor comp)
   int ev_index[16][kMaxT];        // (field, tensor comp) -> combo index or -1
   int nfields;                    // WX_0..WX_{DIM-1}, W, WU_c, WV_c
@@ -42,7 +42,21 @@ struct SFLists {
 struct SFParams {
   KParams k;
   SFLists l;
+  const double* pp[3];            // per axis [nel][9][nq][n*n] products B^{os}(a,q) B^{ot}(b,q)
+  double cconst[kMaxPairs * 9];   // identity geometry + constant form: D'[ij][pair] / JW
+  int const_dp;                   // 1: D'[pair][q] = JW_q * cconst[ij][pair]
 };
+
+// plan-level table: PP[e][os*3+ot][q][a*n+b]
+__global__ void sf_pp_kernel(DevAxis ax, double* __restrict__ out) {
+  const int n = ax.nen, nq = ax.nqp, per = 9 * nq * n * n;
+  const size_t total = (size_t)ax.nel * per;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t / per), r = (int)(t - (size_t)e * per), oo = r / (nq * n * n), r2 = r - oo * nq * n * n, q = r2 / (n * n), ab = r2 - q * n * n, a = ab / n, b = ab - a * n;
+    const double* v = ax.value + ((size_t)(e * nq + q) * n) * 5;
+    out[t] = v[a * 5 + oo / 3] * v[b * 5 + oo % 3];
+  }
+}
 
 __host__ __device__ constexpr int sf_n(int dim, int p, int d) { return d < dim ? p + 1 : 1; }
 
@@ -85,14 +99,16 @@ struct SFCfg {
   static constexpr int THREADS = (G > 256) ? ((G + 31) / 32 * 32) : 256;
 };
 
-template <int DIM, int P, int DOF>
+// NQ > 0: every used axis has exactly NQ quadrature points (the default rule NQ = p+1), loops unroll fully; NQ = 0: runtime
+template <int DIM, int P, int DOF, int NQ>
 __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(const __grid_constant__ SFParams sp) {
   using Cfg = SFCfg<DIM, P, DOF>;
   constexpr int n0 = Cfg::n0, n1 = Cfg::n1, n2 = Cfg::n2, NEN = Cfg::NEN, G = Cfg::G, NEN1 = P + 1;
   const KParams& prm = sp.k;
   const SFLists& ls = sp.l;
   extern __shared__ double smem_all[];
-  const int nq0 = prm.ax[0].nqp, nq1 = prm.ax[1].nqp, nq2 = prm.ax[2].nqp, nqp = nq0 * nq1 * nq2;
+  const int nq0 = (NQ > 0) ? NQ : prm.ax[0].nqp, nq1 = (NQ > 0) ? (DIM > 1 ? NQ : 1) : prm.ax[1].nqp,
+            nq2 = (NQ > 0) ? (DIM > 2 ? NQ : 1) : prm.ax[2].nqp, nqp = nq0 * nq1 * nq2;
   const int NA = prm.mc1 - prm.mc0, NV = prm.vc1 - prm.vc0, NT = ls.NT;
   const SFSmem lay(n0, n1, n2, nq0, nq1, nq2, DIM, DOF, ls, NA, NV, prm.per_qp, prm.c1 - prm.c0);
   const int grp = threadIdx.x / G, lt = threadIdx.x - grp * G;
@@ -205,18 +221,14 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       }
   }
   __syncthreads();
-  if (valid) {  // pair products PP_d[os*3+ot][q][a][b] = B_d^{os}(a,q) B_d^{ot}(b,q)
-    for (int t = lt; t < 9 * nq0 * n0 * n0; t += G) {
-      const int oo = t / (nq0 * n0 * n0), r = t - oo * nq0 * n0 * n0, q = r / (n0 * n0), ab = r - q * n0 * n0, a = ab / n0, b = ab - a * n0;
-      PP0[t] = BD(0, oo / 3, q, a) * BD(0, oo % 3, q, b);
-    }
-    for (int t = lt; t < 9 * nq1 * n1 * n1; t += G) {
-      const int oo = t / (nq1 * n1 * n1), r = t - oo * nq1 * n1 * n1, q = r / (n1 * n1), ab = r - q * n1 * n1, a = ab / n1, b = ab - a * n1;
-      PP1[t] = BD(1, oo / 3, q, a) * BD(1, oo % 3, q, b);
-    }
-    for (int t = lt; t < 9 * nq2 * n2 * n2; t += G) {
-      const int oo = t / (nq2 * n2 * n2), r = t - oo * nq2 * n2 * n2, q = r / (n2 * n2), ab = r - q * n2 * n2, a = ab / n2, b = ab - a * n2;
-      P2[t] = BD(2, oo / 3, q, a) * BD(2, oo % 3, q, b);
+  if (valid) {  // pair products PP_d[os*3+ot][q][a][b] = B_d^{os}(a,q) B_d^{ot}(b,q): per-axis tables built once per plan
+    {
+      const double* g0p = sp.pp[0] + (size_t)ID[0] * 9 * nq0 * n0 * n0;
+      for (int t = lt; t < 9 * nq0 * n0 * n0; t += G) PP0[t] = g0p[t];
+      const double* g1p = sp.pp[1] + (size_t)ID[1] * 9 * nq1 * n1 * n1;
+      for (int t = lt; t < 9 * nq1 * n1 * n1; t += G) PP1[t] = g1p[t];
+      const double* g2p = sp.pp[2] + (size_t)ID[2] * 9 * nq2 * n2 * n2;
+      for (int t = lt; t < 9 * nq2 * n2 * n2; t += G) P2[t] = g2p[t];
     }
     // ---- field evaluation at the points, axis by axis: Ev[c][q] = sum_a psi_t(a,q) F_f[a]  (K5, K11/K12) ----
     for (int t = lt; t < ls.nev * nq0 * n1 * n2; t += G) {
@@ -308,25 +320,22 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       }
       const double jw = J * w;
       JW[q] = jw;
-      // component transformation matrix A[al][s], al = physical component relative to c0
+      // component transformation matrix A[al][s], al = physical component relative to c0, kept in shared memory
       const int NC = prm.c1 - prm.c0;
-      double A[kMaxComp][kMaxT];
-#pragma unroll
-      for (int al = 0; al < kMaxComp; al++)
-#pragma unroll
-        for (int s = 0; s < kMaxT; s++) A[al][s] = 0.0;
+      double* A = Aq + (size_t)q * NC * NT;
+      for (int k = 0; k < NC * NT; k++) A[k] = 0.0;
       for (int al = 0; al < NC; al++) {
         const int c = al + prm.c0;
-        if (c == 0) A[al][ls.tN] = iw;
+        if (c == 0) A[al * NT + ls.tN] = iw;
         else if (c <= DIM) {
           const int i = c - 1;
           double sN = 0.0;
 #pragma unroll
-          for (int d = 0; d < DIM; d++) { A[al][ls.tG[d]] = E[d][i] * iw; sN -= E[d][i] * wg[d]; }
-          if (rational) A[al][ls.tN] = sN * iw * iw;
+          for (int d = 0; d < DIM; d++) { A[al * NT + ls.tG[d]] = E[d][i] * iw; sN -= E[d][i] * wg[d]; }
+          if (rational) A[al * NT + ls.tN] = sN * iw * iw;
         } else {
 #pragma unroll
-          for (int d = 0; d < DIM; d++) A[al][ls.tL[d]] = 1.0;   // Laplacian on the identity map only (host checks)
+          for (int d = 0; d < DIM; d++) A[al * NT + ls.tL[d]] = 1.0;   // Laplacian on the identity map only (host checks)
         }
       }
       // state at the point in physical components (K12): u_al = sum_s A[al][s] * Ev[WU][s]
@@ -336,14 +345,14 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
           double ph[kMaxComp];
           for (int al = 0; al < NC; al++) {
             double s = 0.0;
-            for (int t = 0; t < NT; t++) s += A[al][t] * ev(ls.f_u0 + i, t);
+            for (int t = 0; t < NT; t++) s += A[al * NT + t] * ev(ls.f_u0 + i, t);
             ph[al] = s;
           }
           qp.u[i] = (prm.c0 == 0) ? ph[0] : 0.0;
 #pragma unroll
           for (int d = 0; d < DIM; d++) { const int al = 1 + d - prm.c0; qp.gu[i][d] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
           { const int al = DIM + 1 - prm.c0; qp.d2u[i] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
-          qp.v[i] = (ls.f_v0 >= 0 && prm.c0 == 0) ? A[0][ls.tN] * ev(ls.f_v0 + i, ls.tN) : 0.0;
+          qp.v[i] = (ls.f_v0 >= 0 && prm.c0 == 0) ? A[ls.tN] * ev(ls.f_v0 + i, ls.tN) : 0.0;
         }
       }
       double* C = Cq + (size_t)(prm.per_qp ? q : 0) * DOF * DOF * (NA > 0 ? NA * NA : 1);
@@ -360,13 +369,10 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         for (int i = 0; i < DOF; i++)
           for (int s = 0; s < NT; s++) {
             double acc = 0.0;
-            for (int al = 0; al < NV; al++) acc += A[prm.vc0 - prm.c0 + al][s] * fsrc[i * NV + al];
+            for (int al = 0; al < NV; al++) acc += A[(prm.vc0 - prm.c0 + al) * NT + s] * fsrc[i * NV + al];
             Fp[(i * NT + s) * nqp + q] = acc * jw;
           }
       }
-      // keep A for the matrix passes: [q][NC][NT]
-      for (int al = 0; al < NC; al++)
-        for (int s = 0; s < NT; s++) Aq[(q * NC + al) * NT + s] = A[al][s];
     }
   __syncthreads();
   // constant-coefficient forms: the thread of q==0 filled slot 0 above, but other points may have read it before it was
@@ -430,7 +436,9 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       if (!((ls.ijmask >> ij) & 1)) continue;     // uniform over the grid
       const int bi = ij / DOF, bj = ij - bi * DOF;
       // D'[pair][q] = JW_q * sum_{al,be} A[mc0-c0+al][s] C_q[i][j][al][be] A[mc0-c0+be][t]
-      if (valid)
+      if (valid && sp.const_dp) {
+        for (int t = lt; t < ls.npairs * nqp; t += G) { const int pr = t / nqp, q = t - pr * nqp; Dp[t] = sp.cconst[ij * kMaxPairs + pr] * JW[q]; }
+      } else if (valid)
         for (int t = lt; t < ls.npairs * nqp; t += G) {
           const int pr = t / nqp, q = t - pr * nqp, s = ls.pair_s[pr], tt = ls.pair_t[pr];
           const double* C = Cq + ((size_t)(prm.per_qp ? q : 0) * DOF * DOF + ij) * NA * NA;
@@ -471,8 +479,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         for (int q2 = 0; q2 < nq2; q2++)
           for (int g2 = 0; g2 < ls.ng2; g2++) {
             double u2 = 0.0;
-            for (int g1 = 0; g1 < ls.ng1; g1++) {
-              if (ls.g1_g2[g1] != g2) continue;
+            for (int g1 = ls.g2_first[g2]; g1 < ls.g2_first[g2 + 1]; g1++) {
               const double* pp = PP1 + (size_t)ls.g1_oo1[g1] * nq1 * n1 * n1 + ab1;
               const double* u1 = U1 + ((size_t)(g1 * nq2 + q2) * nq1) * n0 * n0 + ab0;
               for (int q1 = 0; q1 < nq1; q1++) u2 += pp[q1 * n1 * n1] * u1[q1 * n0 * n0];
