@@ -77,9 +77,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_case(mesh, p=3):
+def build_case(mesh, p=3, geometry=None):
     from tests.common import Case
-    return Case(3, p=p, N=mesh, bcv=[(d, s, 0, 1.0) for d in range(3) for s in range(2)])
+    geo = None if geometry in (None, "identity") else ("perturbed", 0.05)     # SURVEY 8d cfg 2g
+    return Case(3, p=p, N=mesh, bcv=[(d, s, 0, 1.0) for d in range(3) for s in range(2)], geometry=geo)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -160,6 +161,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--path", default="auto", choices=["auto", "quadrature"])
     ap.add_argument("--mesh", type=int, default=128)
+    ap.add_argument("--geometry", default="identity", choices=["identity", "perturbed"])
+    ap.add_argument("--quad-impl", type=int, default=0, help="0 = sum-factorised quadrature kernel, 1 = pair-loop kernel")
     ap.add_argument("--cpu-threads", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -197,11 +200,12 @@ def main():
         nccl = comm.value
 
     stream = torch.cuda.Stream()
-    case = build_case(args.mesh)
+    case = build_case(args.mesh, geometry=args.geometry)
     g = case.product(rank=rank, size=world, nccl=nccl, device=local, setup=False)
     g.SetStream(stream.cuda_stream)
     g.SetUp()
     g.SetOption("path", {"auto": 0, "quadrature": 1}[args.path])
+    g.SetOption("quad_impl", args.quad_impl)
     g.SetForm("SYSTEM", "POISSON")
     A, B = g.CreateMat(), g.CreateVec()          # IGACreateMat: pattern built once, outside the timed region
     nnz_local = A.nnz
@@ -294,14 +298,15 @@ def main():
     else:                  # quadrature path: FP64 FMA bound; achieved = W_e x elements / kernel time
         flop = float(W_E) * (nel_global / world)
         roof = {"bound": "fp64", "achieved": flop / (kern_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-                "traffic": None, "kernel": "quad_kernel<3,3,1,4>", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
+                "traffic": None, "kernel": "quad_sf_kernel<3,3,1,4>" if args.quad_impl == 0 else "quad_kernel<3,3,1,4>", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
                 "peak_source": "nominal FP64 FMA peak (148 SM x 64 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no FP64 figure"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     line = {
         "metric": "assembled_Mnnz_per_s", "value": value, "unit": "Mnnz/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "elements_per_s": nel_global / sec,
-        "config": {"workload": "demo/Poisson3D p=3 C2 %d^3 dof=1 AIJ IGAComputeSystem" % args.mesh, "elements": nel_global, "nnz": nnz_global,
+        "config": {"workload": "demo/Poisson3D p=3 C2 %d^3 dof=1 AIJ IGAComputeSystem%s" % (args.mesh, "" if args.geometry == "identity" else " on a mapped geometry (cfg 2g)"),
+                   "elements": nel_global, "nnz": nnz_global,
                    "path": {1: "quadrature", 2: "kronecker"}.get(path_used, str(path_used)),
                    "l2": "each step rewrites the %.2f GB value array (> 126 MB L2)" % (nnz_local * 8 / 1e9),
                    "parallelism": "box partition, %d rank(s)" % world},

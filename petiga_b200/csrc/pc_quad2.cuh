@@ -66,28 +66,28 @@ struct SFSmem {
   __host__ __device__ SFSmem(int n0, int n1, int n2, int nq0, int nq1, int nq2, int dim, int dof, const SFLists& l, int NA, int NV, int per_qp, int NC) {
     const int nqp = nq0 * nq1 * nq2, nen = n0 * n1 * n2;
     int o = 0;
-    b1d = o; o += 3 * (nq0 * n0 + nq1 * n1 + nq2 * n2);                 // B_d[o][q][a], o = 0..2
-    pp0 = o; o += 9 * nq0 * n0 * n0;                                     // PP0[os*3+ot][q0][a0][b0]
-    pp1 = o; o += 9 * nq1 * n1 * n1;
-    p2 = o; o += 9 * nq2 * n2 * n2;
-    dp = o; o += (l.npairs > 0 ? l.npairs : 1) * nqp;                    // D'[pair][q] of the current (i,j) block
-    fp = o; o += dof * l.NT * nqp;                                       // f'[i][s][q]
-    u1 = o; { int a = l.ng1 * nq2 * nq1 * n0 * n0, b = dof * l.NT * nq2 * nq1 * n0; o += (a > b ? a : b) + 1; }   // U1[g1][q2][q1][a0 b0] / R1
-    ev = o; o += (l.nev > 0 ? l.nev : 1) * nqp;                          // evaluated polynomial fields
-    s1 = o; { int a = l.nev * nq0 * n1 * n2, b = dof * l.NT * n0 * nq1 * nq2; o += (a > b ? a : b) + 1; }
-    s2 = o; { int a = l.nev * nq0 * nq1 * n2, b = dof * l.NT * n0 * n1 * nq2; o += (a > b ? a : b) + 1; }
-    aq = o; o += nqp * NC * l.NT;                                        // A_q[al][s]
-    cq = o; o += (per_qp ? nqp : 1) * dof * dof * (NA > 0 ? NA * NA : 1);
-    fq = o; o += (per_qp ? nqp : 1) * dof * (NV > 0 ? NV : 1);
-    fld = o; o += (l.nfields > 0 ? l.nfields : 1) * nen;                 // nodal fields (already multiplied by W_a)
-    fe = o; o += nen * dof;
-    r1 = o; o += 3 * nqp + nqp;                                          // per point: x[3], JW
-    r2 = o; o += nen;                                                    // W_a
-    fixval = o; o += nen * dof;
-    flux = o; o += nen * dof;
-    ufix = o; o += nen * dof;
-    ints = o; o += (nen + nen * dof + 3 * 25 + 3 * 5 + 8) / 2 + 1;
-    total = o;
+    b1d = o; o += (3 * (nq0 * n0 + nq1 * n1 + nq2 * n2)); o += (o & 1);                 // B_d[o][q][a], o = 0..2
+    pp0 = o; o += (9 * nq0 * n0 * n0); o += (o & 1);                                     // PP0[os*3+ot][q0][a0][b0]
+    pp1 = o; o += (9 * nq1 * n1 * n1); o += (o & 1);
+    p2 = o; o += (9 * nq2 * n2 * n2); o += (o & 1);
+    dp = o; o += ((l.npairs > 0 ? l.npairs : 1) * nqp); o += (o & 1);                    // D'[pair][q] of the current (i,j) block
+    fp = o; o += (dof * l.NT * nqp); o += (o & 1);                                       // f'[i][s][q]
+    u1 = o; { int a = l.ng1 * nq2 * nq1 * n0 * n0, b = dof * l.NT * nq2 * nq1 * n0; o += ((a > b ? a : b) + 1); o += (o & 1); }   // U1[g1][q2][q1][a0 b0] / R1
+    ev = o; o += ((l.nev > 0 ? l.nev : 1) * nqp); o += (o & 1);                          // evaluated polynomial fields
+    s1 = o; { int a = l.nev * nq0 * n1 * n2, b = dof * l.NT * n0 * nq1 * nq2; o += ((a > b ? a : b) + 1); o += (o & 1); }
+    s2 = o; { int a = l.nev * nq0 * nq1 * n2, b = dof * l.NT * n0 * n1 * nq2, c = (per_qp ? nqp : 1) * dof * dof * NA * NA; a = a > b ? a : b; o += ((a > c ? a : c) + 1); o += (o & 1); }
+    aq = o; o += (nqp * NC * l.NT); o += (o & 1);                                        // A_q[al][s]
+    cq = o; o += ((per_qp ? nqp : 1) * dof * dof * (NA > 0 ? NA * NA : 1)); o += (o & 1);
+    fq = o; o += ((per_qp ? nqp : 1) * dof * (NV > 0 ? NV : 1)); o += (o & 1);
+    fld = o; o += ((l.nfields > 0 ? l.nfields : 1) * nen); o += (o & 1);                 // nodal fields (already multiplied by W_a)
+    fe = o; o += (nen * dof); o += (o & 1);
+    r1 = o; o += (3 * nqp + nqp); o += (o & 1);                                          // per point: x[3], JW
+    r2 = o; o += (nen); o += (o & 1);                                                    // W_a
+    fixval = o; o += (nen * dof); o += (o & 1);
+    flux = o; o += (nen * dof); o += (o & 1);
+    ufix = o; o += (nen * dof); o += (o & 1);
+    ints = o; o += ((nen + nen * dof + 3 * 25 + 3 * 5 + 8) / 2 + 1); o += (o & 1);
+    total = o + (o & 1);
   }
 };
 
@@ -322,20 +322,20 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       JW[q] = jw;
       // component transformation matrix A[al][s], al = physical component relative to c0, kept in shared memory
       const int NC = prm.c1 - prm.c0;
-      double* A = Aq + (size_t)q * NC * NT;
-      for (int k = 0; k < NC * NT; k++) A[k] = 0.0;
+      double* A = Aq + q;                                   // A[(al*NT+s)*nqp], q fastest: conflict-free across points
+      for (int k = 0; k < NC * NT; k++) A[k * nqp] = 0.0;
       for (int al = 0; al < NC; al++) {
         const int c = al + prm.c0;
-        if (c == 0) A[al * NT + ls.tN] = iw;
+        if (c == 0) A[(al * NT + ls.tN) * nqp] = iw;
         else if (c <= DIM) {
           const int i = c - 1;
           double sN = 0.0;
 #pragma unroll
-          for (int d = 0; d < DIM; d++) { A[al * NT + ls.tG[d]] = E[d][i] * iw; sN -= E[d][i] * wg[d]; }
-          if (rational) A[al * NT + ls.tN] = sN * iw * iw;
+          for (int d = 0; d < DIM; d++) { A[(al * NT + ls.tG[d]) * nqp] = E[d][i] * iw; sN -= E[d][i] * wg[d]; }
+          if (rational) A[(al * NT + ls.tN) * nqp] = sN * iw * iw;
         } else {
 #pragma unroll
-          for (int d = 0; d < DIM; d++) A[al * NT + ls.tL[d]] = 1.0;   // Laplacian on the identity map only (host checks)
+          for (int d = 0; d < DIM; d++) A[(al * NT + ls.tL[d]) * nqp] = 1.0;   // Laplacian on the identity map only (host checks)
         }
       }
       // state at the point in physical components (K12): u_al = sum_s A[al][s] * Ev[WU][s]
@@ -345,22 +345,26 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
           double ph[kMaxComp];
           for (int al = 0; al < NC; al++) {
             double s = 0.0;
-            for (int t = 0; t < NT; t++) s += A[al * NT + t] * ev(ls.f_u0 + i, t);
+            for (int t = 0; t < NT; t++) s += A[(al * NT + t) * nqp] * ev(ls.f_u0 + i, t);
             ph[al] = s;
           }
           qp.u[i] = (prm.c0 == 0) ? ph[0] : 0.0;
 #pragma unroll
           for (int d = 0; d < DIM; d++) { const int al = 1 + d - prm.c0; qp.gu[i][d] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
           { const int al = DIM + 1 - prm.c0; qp.d2u[i] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
-          qp.v[i] = (ls.f_v0 >= 0 && prm.c0 == 0) ? A[ls.tN] * ev(ls.f_v0 + i, ls.tN) : 0.0;
+          qp.v[i] = (ls.f_v0 >= 0 && prm.c0 == 0) ? A[ls.tN * nqp] * ev(ls.f_v0 + i, ls.tN) : 0.0;
         }
       }
-      double* C = Cq + (size_t)(prm.per_qp ? q : 0) * DOF * DOF * (NA > 0 ? NA * NA : 1);
       double* fv = Fq + (size_t)(prm.per_qp ? q : 0) * DOF * (NV > 0 ? NV : 1);
       if (prm.per_qp || q == 0) {
+        // the form writes a dense [DOF][DOF][NA][NA] block; stage it in this point's slice of S2 (free at this time), then
+        // store it with the point index fastest so that the D' pass reads it without bank conflicts
+        double* C = S2 + (size_t)(prm.per_qp ? q : 0) * DOF * DOF * NA * NA;
         for (int k = 0; k < DOF * DOF * NA * NA; k++) C[k] = 0.0;
         for (int k = 0; k < DOF * NV; k++) fv[k] = 0.0;
         form_coefficients<DIM, DOF>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, NA, NV, NA ? C : nullptr, NV ? fv : nullptr);
+        const int cstride = prm.per_qp ? nqp : 1;
+        for (int k = 0; k < DOF * DOF * NA * NA; k++) Cq[(size_t)k * cstride + (prm.per_qp ? q : 0)] = C[k];
       }
       // vector coefficients in tensor components: f'[i][s] = JW * sum_al A[vc0-c0+al][s] f[i][al]
       if (want_vec && NV > 0) {
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         for (int i = 0; i < DOF; i++)
           for (int s = 0; s < NT; s++) {
             double acc = 0.0;
-            for (int al = 0; al < NV; al++) acc += A[(prm.vc0 - prm.c0 + al) * NT + s] * fsrc[i * NV + al];
+            for (int al = 0; al < NV; al++) acc += A[((prm.vc0 - prm.c0 + al) * NT + s) * nqp] * fsrc[i * NV + al];
             Fp[(i * NT + s) * nqp + q] = acc * jw;
           }
       }
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       for (int t = lt; t < nqp * DOF * NT; t += G) {
         const int q = t / (DOF * NT), r = t - q * DOF * NT, i = r / NT, s = r - i * NT;
         double acc = 0.0;
-        for (int al = 0; al < NV; al++) acc += Aq[(q * NC + prm.vc0 - prm.c0 + al) * NT + s] * Fq[i * NV + al];
+        for (int al = 0; al < NV; al++) acc += Aq[((prm.vc0 - prm.c0 + al) * NT + s) * nqp + q] * Fq[i * NV + al];
         Fp[(i * NT + s) * nqp + q] = acc * JW[q];
       }
     }
@@ -441,14 +445,15 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
       } else if (valid)
         for (int t = lt; t < ls.npairs * nqp; t += G) {
           const int pr = t / nqp, q = t - pr * nqp, s = ls.pair_s[pr], tt = ls.pair_t[pr];
-          const double* C = Cq + ((size_t)(prm.per_qp ? q : 0) * DOF * DOF + ij) * NA * NA;
-          const double* Am = Aq + (size_t)(q * NC + prm.mc0 - prm.c0) * NT;
+          const int cstride = prm.per_qp ? nqp : 1;
+          const double* C = Cq + (size_t)ij * NA * NA * cstride + (prm.per_qp ? q : 0);
+          const double* Am = Aq + (size_t)(prm.mc0 - prm.c0) * NT * nqp + q;
           double acc = 0.0;
           for (int al = 0; al < NA; al++) {
-            const double as = Am[al * NT + s];
+            const double as = Am[(al * NT + s) * nqp];
             if (as == 0.0) continue;
             double inner = 0.0;
-            for (int be = 0; be < NA; be++) inner += C[al * NA + be] * Am[be * NT + tt];
+            for (int be = 0; be < NA; be++) inner += C[(al * NA + be) * cstride] * Am[(be * NT + tt) * nqp];
             acc += as * inner;
           }
           Dp[t] = acc * JW[q];
@@ -484,11 +489,19 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
               const double* u1 = U1 + ((size_t)(g1 * nq2 + q2) * nq1) * n0 * n0 + ab0;
               for (int q1 = 0; q1 < nq1; q1++) u2 += pp[q1 * n1 * n1] * u1[q1 * n0 * n0];
             }
-            const double* p2 = P2 + ((size_t)ls.g2_oo2[g2] * nq2 + q2) * n2 * n2;
+            // acc[x][y] += B2^{os}(x,q2) * (B2^{ot}(y,q2) * u2): 2*n2 broadcast loads instead of n2*n2
+            const int oo2 = ls.g2_oo2[g2];
+            const double* bs = &BD(2, oo2 / 3, q2, 0);
+            const double* bt = &BD(2, oo2 % 3, q2, 0);
+            double ty[n2];
 #pragma unroll
-            for (int x = 0; x < n2; x++)
+            for (int y = 0; y < n2; y++) ty[y] = bt[y] * u2;
 #pragma unroll
-              for (int y = 0; y < n2; y++) acc[x][y] = fma(p2[x * n2 + y], u2, acc[x][y]);
+            for (int x = 0; x < n2; x++) {
+              const double bx = bs[x];
+#pragma unroll
+              for (int y = 0; y < n2; y++) acc[x][y] = fma(bx, ty[y], acc[x][y]);
+            }
           }
       }
       // NURBS node weights, fix-up (petigaelem.c:1360-1389,1483-1501) and scatter of this block
