@@ -208,6 +208,7 @@ int petiga_cuda_get_stat(petiga_cuda_plan* P, const char* name, double* value) {
   if (!P || !name || !value) return PETIGA_CUDA_ERR_ARG;
   if (!strcmp(name, "launches")) { *value = (double)P->launches; return 0; }
   if (!strcmp(name, "last_path")) { *value = (double)P->last_path; return 0; }
+  if (!strcmp(name, "last_impl")) { *value = (double)P->last_impl; return 0; }
   if (!strcmp(name, "last_kernel_ms")) { *value = P->last_kernel_ms; return 0; }
   if (!strcmp(name, "num_sms")) { *value = P->num_sms; return 0; }
   if (!strcmp(name, "nghostrows")) { *value = P->L.nghostrows; return 0; }
@@ -368,17 +369,19 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   P->last_path = use_kron ? PETIGA_PATH_KRONECKER : PETIGA_PATH_QUADRATURE;
 
   cudaEventRecord(P->ev0, P->stream);
+  bool quad_mat = want_mat;   // does the quadrature kernel still have to produce the matrix?
   if (use_kron) {   // write-once path: no zeroing, no atomics, no exchange
-    int rc = launch_kronecker(P, slot, block, want_mat ? values : nullptr, want_vec ? rhs : nullptr);
-    cudaEventRecord(P->ev1, P->stream);
-    return rc;
+    const bool hybrid = want_vec && !fi.constant_f;   // e.g. L2Projection: separable mass matrix, point-wise load f(x)
+    int rc = launch_kronecker(P, slot, block, want_mat ? values : nullptr, (want_vec && !hybrid) ? rhs : nullptr);
+    if (rc || !hybrid) { cudaEventRecord(P->ev1, P->stream); return rc; }
+    quad_mat = false;
   }
 
   // MatZeroEntries / VecZeroEntries (petigaksp.c:166-167)
-  if (want_mat) PC_CUDA(cudaMemsetAsync(values, 0, nval * sizeof(double), P->stream));
+  if (quad_mat) PC_CUDA(cudaMemsetAsync(values, 0, nval * sizeof(double), P->stream));
   double* rhs_k = rhs;
   if (multi) {
-    if (want_mat) {
+    if (quad_mat) {
       int rc = ensure(&P->d_ghost_values, &P->ghost_values_cap, (size_t)(L.nnz_loc - L.nnz_own) * bs2);
       if (rc) return rc;
       PC_CUDA(cudaMemsetAsync(P->d_ghost_values, 0, (size_t)(L.nnz_loc - L.nnz_own) * bs2 * sizeof(double), P->stream));
@@ -426,10 +429,10 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
         if (fs.lcount && P->d_X) { set_error("compute: boundary loads on a mapped geometry (BoundaryArea) are not available on the device path yet"); return PETIGA_CUDA_ERR_SUP; }
       }
   kp.form = form; kp.slot = slot; kp.block = block;
-  kp.mc0 = fi.mc0; kp.mc1 = fi.mc1; kp.vc0 = fi.vc0; kp.vc1 = fi.vc1;
+  kp.mc0 = fi.mc0; kp.mc1 = quad_mat ? fi.mc1 : fi.mc0; kp.vc0 = fi.vc0; kp.vc1 = fi.vc1;
   kp.per_qp = fi.per_qp; kp.needs_x = fi.needs_x; kp.needs_state = fi.needs_state || (state && kp.any_bc);
   int c0 = 99, c1 = 0;
-  if (fi.mc1 > fi.mc0) { c0 = std::min(c0, fi.mc0); c1 = std::max(c1, fi.mc1); }
+  if (kp.mc1 > kp.mc0) { c0 = std::min(c0, fi.mc0); c1 = std::max(c1, fi.mc1); }
   if (fi.vc1 > fi.vc0) { c0 = std::min(c0, fi.vc0); c1 = std::max(c1, fi.vc1); }
   if (c1 == 0) { c0 = 0; c1 = 1; }
   if (P->d_X) { c0 = 0; c1 = std::max(c1, 1 + L.dim); }
@@ -437,11 +440,17 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   kp.c0 = c0; kp.c1 = c1;
   memcpy(kp.prm, P->slots[slot].prm, sizeof(kp.prm));
   kp.shift = shift; kp.t = t;
-  int rc = P->quad_impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+  // kernel choice (measured, profiles/r1_configs_1gpu.jsonl): the sum-factorised kernel wins on large elements (3-D, p >= 2:
+  // 6x at cfg 2), the pair-loop kernel on small ones where per-element set-up dominates (5x at cfg 5, 2-D p=2)
+  int impl = P->quad_impl;
+  if (impl < 0) impl = (L.dim == 3 && L.ax[0].p >= 2) ? 0 : 1;
+  int rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+  if (rc == PETIGA_CUDA_ERR_SUP && P->quad_impl < 0) rc = impl == 1 ? launch_quadrature_sf(P, kp) : launch_quadrature(P, kp);
   if (rc) return rc;
+  P->last_impl = impl;
   cudaEventRecord(P->ev1, P->stream);
   if (multi) {
-    rc = exchange_ghost_rows(P, block, values, rhs, want_mat, want_vec);
+    rc = exchange_ghost_rows(P, block, values, rhs, quad_mat, want_vec);
     if (rc) return rc;
   }
   return 0;

@@ -30,10 +30,11 @@ struct FormInfo {
   int needs_state;    // reads U (and V for transient slots)
   int order;          // highest derivative read (0, 1 or 2)
   int constant_f;     // vector coefficient is a constant (eligible for the separable path)
+  int mat_const;      // matrix coefficient tensor does not depend on the point
 };
 
 __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int dof) {
-  FormInfo f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  FormInfo f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool lin = (slot == PETIGA_SLOT_VECTOR || slot == PETIGA_SLOT_MATRIX || slot == PETIGA_SLOT_SYSTEM);
   const bool fun = (slot == PETIGA_SLOT_FUNCTION || slot == PETIGA_SLOT_IFUNCTION);
   const bool jac = (slot == PETIGA_SLOT_JACOBIAN || slot == PETIGA_SLOT_IJACOBIAN);
@@ -75,6 +76,7 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       if (jac) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
       break;
   }
+  f.mat_const = !f.per_qp || form == PETIGA_FORM_L2PROJECTION;
   if (slot == PETIGA_SLOT_VECTOR) { f.mc0 = f.mc1 = 0; }
   if (slot == PETIGA_SLOT_MATRIX) { f.vc0 = f.vc1 = 0; }
   return f;

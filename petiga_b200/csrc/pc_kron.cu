@@ -48,6 +48,7 @@ struct KronParams {
   int gw[3];
   int dim, dof, block, slot, simple;
   int nterms, nvterms, rsmask0;
+  int rsmask_ij[9];       // per (i,j) block: which axis-0 order pairs occur
   KronTerm terms[kMaxTerms];
   KronVTerm vterms[8];
   FixSide bc[3][2];
@@ -259,14 +260,16 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       if (!SIMPLE) { const uint32_t s0 = kp.seg[0][gi * kMaxW + ci]; Bi = s0 & 255; Si = (s0 >> 8) & 255; Li = (s0 >> 16) & 255; }
       const int cci = slow ? bcode(fi + ci, kp.nnp[0], kp.periodic[0]) : 0;
       const bool diag_i = (ci == Ai - fi);
-      const bool rs12 = (DOF > 1) || (kp.rsmask0 & 6);
       for (int cjk = (grp < ngrp) ? grp : Wjk; cjk < Wjk; cjk += ngrp) {
         double v[DOF * DOF];
 #pragma unroll
         for (int ij = 0; ij < DOF * DOF; ij++) {
-          double x = a[0] * G[0][ij][cjk];
-          x = fma(a[3], G[3][ij][cjk], x);
-          if (rs12) { x = fma(a[1], G[1][ij][cjk], x); x = fma(a[2], G[2][ij][cjk], x); }
+          const int m = kp.rsmask_ij[ij];      // uniform: skip the order pairs this block never uses
+          double x = 0.0;
+          if (m & 1) x = a[0] * G[0][ij][cjk];
+          if (m & 8) x = fma(a[3], G[3][ij][cjk], x);
+          if (m & 2) x = fma(a[1], G[1][ij][cjk], x);
+          if (m & 4) x = fma(a[2], G[2][ij][cjk], x);
           v[ij] = x;
         }
         int pos = cjk * Wi + ci;
@@ -362,8 +365,9 @@ void host_terms(int form, int slot, const double* prm, const FormInfo& fi, KronP
   std::vector<double> C((size_t)DOF * DOF * std::max(NA, 1) * std::max(NA, 1), 0.0), fv((size_t)DOF * std::max(NV, 1), 0.0);
   QPoint q;
   memset(&q, 0, sizeof(q));
-  form_coefficients<DIM, DOF>(form, slot, prm, 0.0, 0.0, q, NA, NV, NA ? C.data() : nullptr, NV ? fv.data() : nullptr);
+  form_coefficients<DIM, DOF>(form, slot, prm, 0.0, 0.0, q, NA, NV, NA ? C.data() : nullptr, (NV && fi.constant_f) ? fv.data() : nullptr);
   kp.nterms = kp.nvterms = kp.rsmask0 = 0;
+  for (int k = 0; k < 9; k++) kp.rsmask_ij[k] = 0;
   for (int i = 0; i < DOF; i++)
     for (int j = 0; j < DOF; j++)
       for (int al = 0; al < NA; al++)
@@ -378,6 +382,7 @@ void host_terms(int form, int slot, const double* prm, const FormInfo& fi, KronP
           if (kp.nterms < kMaxTerms) kp.terms[kp.nterms] = t;
           kp.nterms++;
           kp.rsmask0 |= 1 << rs[0];
+          kp.rsmask_ij[i * DOF + j] |= 1 << rs[0];
         }
   for (int i = 0; i < DOF; i++)
     for (int al = 0; al < NV; al++) {
@@ -398,7 +403,13 @@ bool kron_applicable(const petiga_cuda_plan* P, int slot, int form) {
   if (slot != PETIGA_SLOT_VECTOR && slot != PETIGA_SLOT_MATRIX && slot != PETIGA_SLOT_SYSTEM) return false;
   if (P->d_X) return false;                                  // mapped geometry: coefficients vary per point
   FormInfo fi = form_info(form, slot, L.dim, L.dof);
-  if (!fi.valid || fi.per_qp || !fi.constant_f) return false;
+  if (!fi.valid || !fi.mat_const) return false;
+  if (!fi.constant_f) {
+    // point-wise load: the matrix can still be written by this path and the vector integrated by the quadrature kernel,
+    // provided no Dirichlet/Neumann fix-up couples them (IGAComputeMatrix/Vector never fix)
+    if (slot == PETIGA_SLOT_VECTOR) return false;
+    if (slot == PETIGA_SLOT_SYSTEM && P->has_bc) return false;
+  }
   if (L.dof > 3) return false;
   if (P->d_fixtable && L.nranks > 1) return false;          // table values of off-box columns are not local
   for (int d = 0; d < L.dim; d++)

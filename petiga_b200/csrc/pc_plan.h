@@ -63,10 +63,11 @@ struct petiga_cuda_plan {
   struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
   int path = PETIGA_PATH_AUTO;
   int scatter = 0;
-  int quad_impl = 0;              // 0 = sum-factorised kernel (default), 1 = pair-loop kernel
+  int quad_impl = -1;             // -1 = choose by element size, 0 = sum-factorised kernel, 1 = pair-loop kernel
   // stats
   long launches = 0;
   int last_path = 0;
+  int last_impl = 0;
   double last_kernel_ms = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 148;

@@ -7,8 +7,10 @@ MAT_SLOTS = ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN")
 VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION")
 
 
-def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None):
+def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None, quad_impl=None):
     g = g or case.product()
+    if quad_impl is not None:
+        g.SetOption("quad_impl", quad_impl)
     if path is not None:
         g.SetOption("path", {"auto": 0, "quadrature": 1, "kronecker": 2}[path])
     g.SetForm(slot, form, params)
@@ -41,14 +43,14 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
     return out
 
 
-def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12):
+def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12, quad_impl=None):
     """Pattern bit-exact; values / vectors within `tol` relative Frobenius error (north_star: 1e-12)."""
     o = case.oracle()
     if fixtable is not None:
         o.fixtable(fixtable)
     o.setup()
     Ko, Fo = o.assemble(slot, form, params, shift=shift, V=V, t=t, U=U)
-    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable)
+    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable, quad_impl=quad_impl)
     rp_o, ci_o, _ = o.pattern()
     errs = {}
     if Ko is not None:

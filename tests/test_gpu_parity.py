@@ -21,6 +21,9 @@ def dirichlet_all(dim, value=1.0, field=0):
 @pytest.mark.parametrize("path", ["quadrature", "auto"])
 def test_poisson_system(dim, p, N, path):
     case = Case(dim, p=p, N=N, bcv=dirichlet_all(dim))
+    if path == "quadrature":     # both quadrature kernels explicitly (the default picks one by element size)
+        for impl in (0, 1):
+            check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL, quad_impl=impl)
     res, _ = check_against_oracle(case, "SYSTEM", "POISSON", path=path, tol=TOL)
     assert res["path"] == (2 if path == "auto" else 1)      # identity geometry + constant form -> separable path
 
@@ -78,6 +81,8 @@ def test_elasticity3d(mattype, path):
     case = Case(3, dof=3, p=2, N=(5, 4, 4), bcv=bcv, mattype=mattype)
     res, _ = check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[1.0, 1.0], path=path, tol=TOL)
     check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[2.5, 0.7], path=path, tol=TOL)   # exercises the mu*mu term
+    if path == "quadrature":
+        check_against_oracle(case, "SYSTEM", "ELASTICITY3D", params=[2.5, 0.7], path=path, tol=TOL, quad_impl=1)
 
 
 # ---- F5 Elasticity (dim-generic) with a Neumann load: AddFlux / BoundaryArea ------------------------------
@@ -97,8 +102,9 @@ def test_cahnhilliard2d(N):
     n = N * N
     U, V = state_vectors(n)
     prm = [1.5, 3000.0]
-    check_against_oracle(case, "IFUNCTION", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL)
-    check_against_oracle(case, "IJACOBIAN", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL)
+    for impl in (0, 1):
+        check_against_oracle(case, "IFUNCTION", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL, quad_impl=impl)
+        check_against_oracle(case, "IJACOBIAN", "CAHNHILLIARD2D", prm, U=U, V=V, shift=1.0e3, tol=TOL, quad_impl=impl)
 
 
 # ---- SNES / TS drivers with Dirichlet data: Bratu and the Poisson residual --------------------------------
@@ -137,6 +143,8 @@ def test_fixtable():
 @pytest.mark.parametrize("dim,p,N", [(2, 2, 6), (2, 3, 5), (3, 2, 4), (3, 3, 4)])
 def test_mapped_geometry_poisson(dim, p, N):
     case = Case(dim, p=p, N=N, geometry=("perturbed", 0.05), bcv=dirichlet_all(dim))
+    for impl in (0, 1):
+        check_against_oracle(case, "SYSTEM", "POISSON", tol=TOL, quad_impl=impl)
     res, _ = check_against_oracle(case, "SYSTEM", "POISSON", tol=TOL)
     assert res["path"] == 1     # mapped geometry can only take the quadrature path
 
