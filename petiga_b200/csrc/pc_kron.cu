@@ -46,7 +46,7 @@ struct KronParams {
   const int* localrow;    // ghost box -> local row (for the fix table)
   const double* fixtable; // [ghost box][dof] or NULL
   int gw[3];
-  int dim, dof, block, slot, simple;
+  int dim, dof, block, slot, simple, wfull0;
   int nterms, nvterms, rsmask0;
   int rsmask_ij[9];       // per (i,j) block: which axis-0 order pairs occur
   KronTerm terms[kMaxTerms];
@@ -132,7 +132,8 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 
 // One CTA per (A_j, A_k) pencil of owned rows; warps walk the rows A_i of the pencil; lanes walk the entries of a
 // row in storage order, so every store instruction writes 256 contiguous bytes.
-template <int DOF>
+// PF > 0: all axes have degree PF, so a full-width interior row has compile-time extents and its loop unrolls completely
+template <int DOF, int PF>
 __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ KronParams kp) {
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
@@ -190,6 +191,9 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   const bool vsimple = want_vec && DOF == 1 && kp.nvterms == 1;
   const double vjk = vsimple ? kp.vterms[0].c * kp.mv[1][kp.vterms[0].r1 * kp.nnp[1] + Aj] * kp.mv[2][kp.vterms[0].r2 * kp.nnp[2] + Ak] : 0.0;
   const double* __restrict__ mv0 = kp.mv[0] + (vsimple ? kp.vterms[0].r0 * nnp0 : 0);
+  // full-width rows (W_i = 2p+1, all but the first/last p rows of a pencil): lane -> (column offset, group) fixed per warp
+  const int WiF = kp.wfull0, ngrpF = 32 / WiF, grpF = lane / WiF, ciF = lane - grpF * WiF;
+  const int ostepF = ngrpF * WiF, offF = grpF * WiF + ciF, nfullF = Wjk / ngrpF;   // every group runs nfullF full iterations
   for (int il = warp; il < lw0; il += nwarps) {
     const int Ai = ls0 + il, gi = Ai - gs0;
     const int Wi = __ldg(Wg0 + gi), fi = __ldg(first0 + Ai), W = Wi * Wjk;
@@ -201,18 +205,39 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
       if (!rowb && !colb) {
         // interior row: out[cjk*Wi + ci] = M00_i[ci]*G0[cjk] + M11_i[ci]*G3[cjk]; lane = (ci, group), groups stride cjk
-        const unsigned inv = (65536u + Wi - 1) / Wi;
-        const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
-        if (grp < ngrp) {
-          const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
-          double* out = values + base + grp * Wi + ci;
-          const double* g0 = &G[0][0][grp];
-          const double* g3 = &G[3][0][grp];
-          const int ostep = ngrp * Wi;
-#pragma unroll 4
-          for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
-            *out = fma(a3, *g3, a0 * *g0);
-            out += ostep; g0 += ngrp; g3 += ngrp;
+        constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC;
+        if (PF > 0 && Wi == WIC && Wjk == WJKC) {   // full-width row of an interior pencil: everything but (a0, a3, base) is static
+          if (grpF < NGRP) {
+            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ciF), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ciF);
+            double* __restrict__ rowp = values + base + offF;
+            const double* __restrict__ g0 = &G[0][0][grpF];
+            const double* __restrict__ g3 = &G[3][0][grpF];
+#pragma unroll
+            for (int k = 0; k < NITER; k++)
+              if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) rowp[k * OSTEP] = fma(a3, g3[k * NGRP], a0 * g0[k * NGRP]);
+          }
+        } else if (Wi == WiF) {   // full-width row: lane mapping and trip count hoisted out of the row loop
+          if (grpF < ngrpF) {
+            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ciF), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ciF);
+            double* __restrict__ rowp = values + base + offF;
+            int cjk = grpF;
+            for (int it = 0; it < nfullF; ++it) {
+              *rowp = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+              rowp += ostepF; cjk += ngrpF;
+            }
+            if (cjk < Wjk) *rowp = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+          }
+        } else {
+          const unsigned inv = (65536u + Wi - 1) / Wi;
+          const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
+          if (grp < ngrp) {
+            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
+            double* out = values + base + grp * Wi + ci;
+            const int ostep = ngrp * Wi;
+            for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+              *out = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+              out += ostep;
+            }
           }
         }
         if (want_vec && lane == 0) {
@@ -227,6 +252,69 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
           }
         }
         continue;
+      }
+      if (!kp.fixtable) {
+        // boundary rows of the scalar case (constant Dirichlet values)
+        const int rci0 = bcode(Ai, nnp0, per0);
+        bool rf[1]; double rv[1];
+        node_fix<1>(kp, rci0, rcj, rck, rf, rv);
+        const double nel = (double)(kp.nsup[0][Ai] * kp.nsup[1][Aj] * kp.nsup[2][Ak]);
+        double* __restrict__ rowp = values + base;
+        double racc0 = 0.0;
+        if (rowb && rf[0]) {
+          // fixed row: zero except the diagonal, which counts the elements containing the node (petigaelem.c:1377-1387)
+          const int ediag = ((Ak - fk) * Wj + (Aj - fj)) * Wi + (Ai - fi);
+          for (int e = lane; e < W; e += 32) rowp[e] = (e == ediag) ? nel : 0.0;
+          if (want_vec && lane == 0) rhs[lr] = nel * rv[0];
+          continue;
+        }
+        {  // free row with columns on Dirichlet faces: those entries move to the right-hand side
+          const unsigned inv = (65536u + Wi - 1) / Wi;
+          const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
+          if (grp < ngrp) {
+            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
+            const int cci = bcode(fi + ci, nnp0, per0);
+            double* out = rowp + grp * Wi + ci;
+            const int ostep = ngrp * Wi;
+            for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+              double v = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+              const int info = jkinfo[cjk];
+              if (cci | (info & 15)) {
+                bool cf[1]; double cv[1];
+                node_fix<1>(kp, cci, info & 3, (info >> 2) & 3, cf, cv);
+                if (cf[0]) { racc0 -= v * cv[0]; v = 0.0; }
+              }
+              *out = v;
+              out += ostep;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) racc0 += __shfl_xor_sync(0xffffffffu, racc0, o);
+          if (want_vec && lane == 0) {
+            double F = 0.0;
+            for (int n = 0; n < kp.nvterms; n++) {
+              const KronVTerm vt = kp.vterms[n];
+              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+            }
+            if (rowb) {   // loads on the faces this (unfixed) node lies on
+              const int rcode[3] = {rci0, rcj, rck};
+              for (int d = 0; d < kp.dim; d++) {
+                if (!rcode[d]) continue;
+                const FixSide& fs = kp.bc[d][rcode[d] - 1];
+                if (!fs.lcount) continue;
+                double A = 1.0;
+                if (kp.dim > 1) {
+                  const int An[3] = {Ai, Aj, Ak};
+                  for (int e2 = 0; e2 < kp.dim; e2++) if (e2 != d) A *= kp.lsum[e2][An[e2]];
+                  A *= (kp.dim == 2) ? 2 : 4;
+                }
+                for (int k = 0; k < fs.lcount; k++) if (fs.lfield[k] == 0) F += fs.lvalue[k] * A;
+              }
+            }
+            rhs[lr] = F + racc0;
+          }
+          continue;
+        }
       }
     }
     const int rci = bcode(Ai, kp.nnp[0], kp.periodic[0]);
@@ -276,7 +364,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
         if (!SIMPLE || slow) {
           const int info = jkinfo[cjk];
           if (!SIMPLE) pos = jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li;
-          if (slow) {   // boundary rows / boundary columns only
+          if (slow && (row_boundary || cci || (info & 15))) {   // fixed row, or a column node on a Dirichlet face
             bool cfix[DOF];
             double cval[DOF];
             node_fix<DOF>(kp, cci, info & 3, (info >> 2) & 3, cfix, cval);
@@ -448,7 +536,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
     if (L.ax[d].periodic) simple = false;
   }
   kp.rowbase = P->d_rowbase; kp.localrow = P->d_localrow; kp.fixtable = P->d_fixtable;
-  kp.dim = L.dim; kp.dof = L.dof; kp.block = block; kp.slot = slot; kp.simple = simple;
+  kp.dim = L.dim; kp.dof = L.dof; kp.block = block; kp.slot = slot; kp.simple = simple; kp.wfull0 = 2 * L.ax[0].p + 1;
   kp.values = values; kp.rhs = rhs;
   const double* prm = P->slots[slot].prm;
 #define HT(DIM_, DOF_) if (L.dim == DIM_ && L.dof == DOF_) host_terms<DIM_, DOF_>(form, slot, prm, fi, kp);
@@ -473,11 +561,11 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
       }
   const int blocks = L.ax[1].lw * L.ax[2].lw;
   const int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
-#define KL(DOF_)                                                                              \
-  if (L.dof == DOF_) {                                                                        \
-    kron_rows_kernel<DOF_><<<blocks, threads, 0, P->stream>>>(kp);                            \
-  }
-  KL(1) KL(2) KL(3)
+  int pf = L.ax[0].p;
+  for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
+  if (L.dim < 3 || L.dof != 1) pf = 0;
+#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) kron_rows_kernel<DOF_, PF_><<<blocks, threads, 0, P->stream>>>(kp);
+  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0)
 #undef KL
   PC_CUDA(cudaGetLastError());
   P->launches++;
