@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
+  __shared__ double stage[(DOF > 1) ? 8 * 32 * DOF * DOF : 1];
   const int Aj = kp.ls[1] + (int)(blockIdx.x % kp.lw[1]), Ak = kp.ls[2] + (int)(blockIdx.x / kp.lw[1]);
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
   const int Wj = kp.Wg[1][gj], Wk = kp.Wg[2][gk], Wjk = Wj * Wk;
@@ -348,8 +349,18 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       if (!SIMPLE) { const uint32_t s0 = kp.seg[0][gi * kMaxW + ci]; Bi = s0 & 255; Si = (s0 >> 8) & 255; Li = (s0 >> 16) & 255; }
       const int cci = slow ? bcode(fi + ci, kp.nnp[0], kp.periodic[0]) : 0;
       const bool diag_i = (ci == Ai - fi);
-      for (int cjk = (grp < ngrp) ? grp : Wjk; cjk < Wjk; cjk += ngrp) {
+      // BAIJ blocks of the ngrp*Wi entries a warp produces per iteration are contiguous in memory when the row is in
+      // storage order: stage them in shared memory and write them back with full 256-byte warp stores
+      const bool staged = (DOF > 1) && want_mat && kp.block && SIMPLE;
+      double* stg = (DOF > 1) ? &stage[(threadIdx.x >> 5) * 32 * DOF * DOF] : nullptr;
+      for (int cjk0 = 0; cjk0 < Wjk; cjk0 += ngrp) {
+        const int cjk = cjk0 + grp;
+        const bool act = grp < ngrp && cjk < Wjk;
+        if (!act && !staged) continue;
         double v[DOF * DOF];
+#pragma unroll
+        for (int ij = 0; ij < DOF * DOF; ij++) v[ij] = 0.0;
+        if (act) {
 #pragma unroll
         for (int ij = 0; ij < DOF * DOF; ij++) {
           const int m = kp.rsmask_ij[ij];      // uniform: skip the order pairs this block never uses
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
               }
           }
         }
-        if (want_mat) {
+        if (want_mat && !staged) {
           if (DOF == 1) kp.values[(size_t)(base + pos)] = v[0];
           else {
 #pragma unroll
@@ -400,6 +411,20 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
                 kp.values[off] = v[i * DOF + j];
               }
           }
+        }
+        }   // act
+        if (staged) {   // uniform over the warp
+          const int e0 = cjk0 * Wi, ne = min(ngrp * Wi, W - e0);          // entries [e0, e0+ne) of the row, contiguous blocks
+          if (act) {
+#pragma unroll
+            for (int i = 0; i < DOF; i++)
+#pragma unroll
+              for (int j = 0; j < DOF; j++) stg[lane * DOF * DOF + j * DOF + i] = v[i * DOF + j];   // column-major block
+          }
+          __syncwarp();
+          double* dst = kp.values + (size_t)(base + e0) * DOF * DOF;
+          for (int t = lane; t < ne * DOF * DOF; t += 32) dst[t] = stg[t];
+          __syncwarp();
         }
       }
     }
