@@ -95,6 +95,20 @@ int build_sf_lists(const KParams& kp, const FormInfo& fi, bool mapped, bool rati
     for (int k = 0; k < n; k++) { l.g1_oo1[k] = oo1[k]; l.g1_g2[k] = gg2[k]; }
     for (int k = 0; k < l.npairs; k++) l.pair_g1[k] = (unsigned char)inv[l.pair_g1[k]];
   }
+  {  // order the pairs by g1 group (stage A walks a contiguous range per output) and cache their axis-0 order pair
+    int perm[kMaxPairs], n = 0;
+    for (int g1 = 0; g1 < l.ng1; g1++) {
+      l.g1_first[g1] = (unsigned char)n;
+      for (int k = 0; k < l.npairs; k++) if (l.pair_g1[k] == g1) perm[n++] = k;
+    }
+    l.g1_first[l.ng1] = (unsigned char)n;
+    unsigned char ps[kMaxPairs], pt[kMaxPairs], pg[kMaxPairs];
+    for (int k = 0; k < n; k++) { ps[k] = l.pair_s[perm[k]]; pt[k] = l.pair_t[perm[k]]; pg[k] = l.pair_g1[perm[k]]; }
+    for (int k = 0; k < n; k++) {
+      l.pair_s[k] = ps[k]; l.pair_t[k] = pt[k]; l.pair_g1[k] = pg[k];
+      l.pair_oo0[k] = (unsigned char)(l.torder[ps[k]][0] * 3 + l.torder[pt[k]][0]);
+    }
+  }
   l.ijmask = ijmask;
   // fields and evaluation combos
   for (int f = 0; f < 16; f++) for (int t = 0; t < kMaxT; t++) l.ev_index[f][t] = -1;

@@ -28,8 +28,8 @@ struct SFLists {
   int NT;
   int tN, tG[3], tL[3];           // tensor index of N / d_d / d_dd, or -1
   int torder[kMaxT][3];
-  int npairs; unsigned char pair_s[kMaxPairs], pair_t[kMaxPairs], pair_g1[kMaxPairs];
-  int ng1; unsigned char g1_oo1[kMaxPairs], g1_g2[kMaxPairs];
+  int npairs; unsigned char pair_s[kMaxPairs], pair_t[kMaxPairs], pair_g1[kMaxPairs], pair_oo0[kMaxPairs];
+  int ng1; unsigned char g1_oo1[kMaxPairs], g1_g2[kMaxPairs], g1_first[kMaxPairs + 1];   // pairs of g1 are [g1_first[g1], g1_first[g1+1])
   int ng2; unsigned char g2_oo2[9]; unsigned char g2_first[10];   // g1 groups of g2 are [g2_first[g2], g2_first[g2+1])
   int nev; unsigned char ev_field[kMaxEval], ev_t[kMaxEval];   // evaluation combos (field, tensor comp)
   int ev_index[16][kMaxT];        // (field, tensor comp) -> combo index or -1
@@ -62,7 +62,7 @@ __host__ __device__ constexpr int sf_n(int dim, int p, int d) { return d < dim ?
 
 // shared-memory carve-up of one element slot (offsets in doubles)
 struct SFSmem {
-  int b1d, pp0, pp1, p2, dp, fp, u1, ev, s1, s2, aq, cq, fq, fld, fe, r1, r2, fixval, flux, ufix, ints, total;
+  int b1d, pp0, pp1, p2, dp, fp, u1, ev, s1, s2, aq, cq, fq, fld, fe, r1, r2, geo, fixval, flux, ufix, ints, total;
   __host__ __device__ SFSmem(int n0, int n1, int n2, int nq0, int nq1, int nq2, int dim, int dof, const SFLists& l, int NA, int NV, int per_qp, int NC) {
     const int nqp = nq0 * nq1 * nq2, nen = n0 * n1 * n2;
     int o = 0;
@@ -83,6 +83,7 @@ struct SFSmem {
     fe = o; o += (nen * dof); o += (o & 1);
     r1 = o; o += (3 * nqp + nqp); o += (o & 1);                                          // per point: x[3], JW
     r2 = o; o += (nen); o += (o & 1);                                                    // W_a
+    geo = o; o += (nqp * 13); o += (o & 1);                                             // per point: E[3][3], 1/w, grad w
     fixval = o; o += (nen * dof); o += (o & 1);
     flux = o; o += (nen * dof); o += (o & 1);
     ufix = o; o += (nen * dof); o += (o & 1);
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
   double *B1d = sm + lay.b1d, *PP0 = sm + lay.pp0, *PP1 = sm + lay.pp1, *P2 = sm + lay.p2, *Dp = sm + lay.dp, *Fp = sm + lay.fp;
   double *U1 = sm + lay.u1, *Ev = sm + lay.ev, *S1 = sm + lay.s1, *S2 = sm + lay.s2, *Aq = sm + lay.aq, *Cq = sm + lay.cq, *Fq = sm + lay.fq;
   double *Fld = sm + lay.fld, *Fe = sm + lay.fe, *Xq = sm + lay.r1, *JW = sm + lay.r1 + 3 * nqp, *We = sm + lay.r2;
-  double *FixVal = sm + lay.fixval, *Flux = sm + lay.flux, *UFix = sm + lay.ufix;
+  double *FixVal = sm + lay.fixval, *Flux = sm + lay.flux, *UFix = sm + lay.ufix, *Geo = sm + lay.geo;
   int* lrow = reinterpret_cast<int*>(sm + lay.ints);
   int* fixflag = lrow + NEN;
   uint32_t* segs = reinterpret_cast<uint32_t*>(fixflag + NEN * DOF);
@@ -267,30 +268,28 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
 
   // ---------------- per point: geometry, weights, state, coefficient tensors in parametric components ----------------
   // A[al][s]: physical component al of the (rational, mapped) shape function of node a = W_a * sum_s A[al][s] psi_s(a,q)
+  const int NC = prm.c1 - prm.c0;
+  // (1) one thread per point: weights, NURBS denominator, geometry map and its inverse (K4-K6)
   if (valid)
     for (int q = lt; q < nqp; q += G) {
       const int qi[3] = {q % nq0, (q / nq0) % nq1, q / (nq0 * nq1)};
-      double w = 1.0, J = 1.0;
-      QPoint qp;
-#pragma unroll
-      for (int d = 0; d < 3; d++) qp.x[d] = 0.0;
+      double w = 1.0, J = 1.0, x[3] = {0, 0, 0};
 #pragma unroll
       for (int d = 0; d < DIM; d++) {
         w *= prm.ax[d].weight[ID[d] * nQ[d] + qi[d]];
         J *= prm.ax[d].detJac[ID[d]];
-        qp.x[d] = prm.ax[d].point[ID[d] * nQ[d] + qi[d]];
+        x[d] = prm.ax[d].point[ID[d] * nQ[d] + qi[d]];
       }
       auto ev = [&](int field, int tc) -> double {
         if (field < 0 || tc < 0) return 0.0;
         const int c = ls.ev_index[field][tc];
         return c >= 0 ? Ev[c * nqp + q] : 0.0;
       };
-      // NURBS denominator and its parametric gradient
       double w0 = 1.0, wg[3] = {0, 0, 0};
       if (rational) {
         w0 = ev(ls.f_w, ls.tN);
 #pragma unroll
-        for (int d = 0; d < DIM; d++) wg[d] = ls.tG[d] >= 0 ? ev(ls.f_w, ls.tG[d]) : 0.0;
+        for (int d = 0; d < DIM; d++) wg[d] = ev(ls.f_w, ls.tG[d]);
       }
       const double iw = 1.0 / w0;
       double E[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};   // E[d][i] = du_d/dx_i
@@ -298,11 +297,10 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         double X0[3] = {0, 0, 0}, X1[3][3];                  // X1[i][d] = dX_i/du_d
 #pragma unroll
         for (int i = 0; i < DIM; i++) {
-          const double n0v = ls.tN >= 0 ? ev(ls.f_x0 + i, ls.tN) : 0.0;
-          X0[i] = n0v * iw;
+          X0[i] = ev(ls.f_x0 + i, ls.tN) * iw;
 #pragma unroll
           for (int d = 0; d < DIM; d++) X1[i][d] = (ev(ls.f_x0 + i, ls.tG[d]) - X0[i] * wg[d]) * iw;   // quotient rule (K4) on W*X
-          qp.x[i] = X0[i];
+          x[i] = X0[i];
         }
         double det;
         if (DIM == 1) { det = X1[0][0]; E[0][0] = 1.0 / det; }
@@ -318,79 +316,88 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         }
         J *= det;                                            // detJac *= detX (petigaelem.c:1024-1029)
       }
-      const double jw = J * w;
-      JW[q] = jw;
-      // component transformation matrix A[al][s], al = physical component relative to c0, kept in shared memory
-      const int NC = prm.c1 - prm.c0;
-      double* A = Aq + q;                                   // A[(al*NT+s)*nqp], q fastest: conflict-free across points
-      for (int k = 0; k < NC * NT; k++) A[k * nqp] = 0.0;
-      for (int al = 0; al < NC; al++) {
-        const int c = al + prm.c0;
-        if (c == 0) A[(al * NT + ls.tN) * nqp] = iw;
-        else if (c <= DIM) {
-          const int i = c - 1;
+      JW[q] = J * w;
+#pragma unroll
+      for (int d = 0; d < 3; d++) Xq[d * nqp + q] = x[d];
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) Geo[(d * 3 + i) * nqp + q] = E[d][i];
+      Geo[9 * nqp + q] = iw;
+#pragma unroll
+      for (int d = 0; d < 3; d++) Geo[(10 + d) * nqp + q] = wg[d];
+    }
+  __syncthreads();
+  // (2) all threads: component transformation matrix A[al][s][q]
+  if (valid)
+    for (int t = lt; t < NC * NT * nqp; t += G) {
+      const int q = t % nqp, r = t / nqp, s = r % NT, al = r / NT, c = al + prm.c0;
+      const double iw = Geo[9 * nqp + q];
+      double v = 0.0;
+      if (c == 0) v = (s == ls.tN) ? iw : 0.0;
+      else if (c <= DIM) {
+        const int i = c - 1;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) if (s == ls.tG[d]) v = Geo[(d * 3 + i) * nqp + q] * iw;
+        if (rational && s == ls.tN) {
           double sN = 0.0;
 #pragma unroll
-          for (int d = 0; d < DIM; d++) { A[(al * NT + ls.tG[d]) * nqp] = E[d][i] * iw; sN -= E[d][i] * wg[d]; }
-          if (rational) A[(al * NT + ls.tN) * nqp] = sN * iw * iw;
-        } else {
-#pragma unroll
-          for (int d = 0; d < DIM; d++) A[(al * NT + ls.tL[d]) * nqp] = 1.0;   // Laplacian on the identity map only (host checks)
+          for (int d = 0; d < DIM; d++) sN -= Geo[(d * 3 + i) * nqp + q] * Geo[(10 + d) * nqp + q];
+          v = sN * iw * iw;
         }
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) if (s == ls.tL[d]) v = 1.0;   // Laplacian on the identity map only (host checks)
       }
-      // state at the point in physical components (K12): u_al = sum_s A[al][s] * Ev[WU][s]
+      Aq[t] = v;
+    }
+  __syncthreads();
+  // (3) one thread per point (only the points that need it): state (K12) and the form's coefficient tensors
+  if (valid)
+    for (int q = lt; q < nqp; q += G) {
+      if (!(prm.per_qp || q == 0)) continue;
+      QPoint qp;
+#pragma unroll
+      for (int d = 0; d < 3; d++) qp.x[d] = Xq[d * nqp + q];
       if (state) {
+        const double* A = Aq + q;
 #pragma unroll
         for (int i = 0; i < DOF; i++) {
           double ph[kMaxComp];
           for (int al = 0; al < NC; al++) {
-            double s = 0.0;
-            for (int t = 0; t < NT; t++) s += A[(al * NT + t) * nqp] * ev(ls.f_u0 + i, t);
-            ph[al] = s;
+            double sacc = 0.0;
+            for (int t = 0; t < NT; t++) { const int c = ls.ev_index[ls.f_u0 + i][t]; if (c >= 0) sacc += A[(al * NT + t) * nqp] * Ev[c * nqp + q]; }
+            ph[al] = sacc;
           }
           qp.u[i] = (prm.c0 == 0) ? ph[0] : 0.0;
 #pragma unroll
           for (int d = 0; d < DIM; d++) { const int al = 1 + d - prm.c0; qp.gu[i][d] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
           { const int al = DIM + 1 - prm.c0; qp.d2u[i] = (al >= 0 && al < NC) ? ph[al] : 0.0; }
-          qp.v[i] = (ls.f_v0 >= 0 && prm.c0 == 0) ? A[ls.tN * nqp] * ev(ls.f_v0 + i, ls.tN) : 0.0;
+          qp.v[i] = 0.0;
+          if (ls.f_v0 >= 0 && prm.c0 == 0) { const int c = ls.ev_index[ls.f_v0 + i][ls.tN]; if (c >= 0) qp.v[i] = A[ls.tN * nqp] * Ev[c * nqp + q]; }
         }
       }
       double* fv = Fq + (size_t)(prm.per_qp ? q : 0) * DOF * (NV > 0 ? NV : 1);
-      if (prm.per_qp || q == 0) {
-        // the form writes a dense [DOF][DOF][NA][NA] block; stage it in this point's slice of S2 (free at this time), then
-        // store it with the point index fastest so that the D' pass reads it without bank conflicts
-        double* C = S2 + (size_t)(prm.per_qp ? q : 0) * DOF * DOF * NA * NA;
-        for (int k = 0; k < DOF * DOF * NA * NA; k++) C[k] = 0.0;
-        for (int k = 0; k < DOF * NV; k++) fv[k] = 0.0;
-        form_coefficients<DIM, DOF>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, NA, NV, NA ? C : nullptr, NV ? fv : nullptr);
-        const int cstride = prm.per_qp ? nqp : 1;
-        for (int k = 0; k < DOF * DOF * NA * NA; k++) Cq[(size_t)k * cstride + (prm.per_qp ? q : 0)] = C[k];
-      }
-      // vector coefficients in tensor components: f'[i][s] = JW * sum_al A[vc0-c0+al][s] f[i][al]
-      if (want_vec && NV > 0) {
-        const double* fsrc = Fq + (size_t)(prm.per_qp ? q : 0) * DOF * NV;
-        if (!prm.per_qp && q != 0) { /* slot 0 written by the thread of q == 0 in an earlier pass; see sync below */ }
-        for (int i = 0; i < DOF; i++)
-          for (int s = 0; s < NT; s++) {
-            double acc = 0.0;
-            for (int al = 0; al < NV; al++) acc += A[((prm.vc0 - prm.c0 + al) * NT + s) * nqp] * fsrc[i * NV + al];
-            Fp[(i * NT + s) * nqp + q] = acc * jw;
-          }
-      }
+      // the form writes a dense [DOF][DOF][NA][NA] block; stage it in this point's slice of S2 (free at this time), then
+      // store it with the point index fastest so that the D' pass reads it without bank conflicts
+      double* C = S2 + (size_t)(prm.per_qp ? q : 0) * DOF * DOF * NA * NA;
+      for (int k = 0; k < DOF * DOF * NA * NA; k++) C[k] = 0.0;
+      for (int k = 0; k < DOF * NV; k++) fv[k] = 0.0;
+      form_coefficients<DIM, DOF>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, NA, NV, NA ? C : nullptr, NV ? fv : nullptr);
+      const int cstride = prm.per_qp ? nqp : 1;
+      for (int k = 0; k < DOF * DOF * NA * NA; k++) Cq[(size_t)k * cstride + (prm.per_qp ? q : 0)] = C[k];
     }
   __syncthreads();
-  // constant-coefficient forms: the thread of q==0 filled slot 0 above, but other points may have read it before it was
-  // written; redo the vector coefficients now that the slot is visible
-  if (!prm.per_qp && want_vec && NV > 0) {   // uniform over the CTA
-    if (valid) {
-      const int NC = prm.c1 - prm.c0;
+  // (4) all threads: vector coefficients in tensor components f'[i][s][q] = JW_q * sum_al A[vc0-c0+al][s][q] f_q[i][al]
+  if (want_vec && NV > 0) {   // uniform over the CTA
+    if (valid)
       for (int t = lt; t < nqp * DOF * NT; t += G) {
-        const int q = t / (DOF * NT), r = t - q * DOF * NT, i = r / NT, s = r - i * NT;
+        const int q = t % nqp, r = t / nqp, s = r % NT, i = r / NT;
+        const double* fsrc = Fq + (size_t)(prm.per_qp ? q : 0) * DOF * NV + i * NV;
         double acc = 0.0;
-        for (int al = 0; al < NV; al++) acc += Aq[((prm.vc0 - prm.c0 + al) * NT + s) * nqp + q] * Fq[i * NV + al];
+        for (int al = 0; al < NV; al++) acc += Aq[((prm.vc0 - prm.c0 + al) * NT + s) * nqp + q] * fsrc[al];
         Fp[(i * NT + s) * nqp + q] = acc * JW[q];
       }
-    }
     __syncthreads();
   }
 
@@ -435,7 +442,6 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
   const int ab0 = a0 * n0 + b0, ab1 = a1 * n1 + b1;
   const bool fix_mat = (prm.slot == PETIGA_SLOT_SYSTEM || prm.slot == PETIGA_SLOT_JACOBIAN || prm.slot == PETIGA_SLOT_IJACOBIAN);
   if (want_mat) {
-    const int NC = prm.c1 - prm.c0;
     for (int ij = 0; ij < DOF * DOF; ij++) {
       if (!((ls.ijmask >> ij) & 1)) continue;     // uniform over the grid
       const int bi = ij / DOF, bj = ij - bi * DOF;
@@ -464,9 +470,8 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
         for (int t = lt; t < ls.ng1 * nq2 * nq1 * n0 * n0; t += G) {
           const int g1 = t / (nq2 * nq1 * n0 * n0), r = t - g1 * nq2 * nq1 * n0 * n0, q12 = r / (n0 * n0), ab = r - q12 * n0 * n0;
           double acc = 0.0;
-          for (int pr = 0; pr < ls.npairs; pr++) {
-            if (ls.pair_g1[pr] != g1) continue;
-            const int oo = ls.torder[ls.pair_s[pr]][0] * 3 + ls.torder[ls.pair_t[pr]][0];
+          for (int pr = ls.g1_first[g1]; pr < ls.g1_first[g1 + 1]; pr++) {
+            const int oo = ls.pair_oo0[pr];
             const double* pp = PP0 + (size_t)oo * nq0 * n0 * n0 + ab;
             const double* dq = Dp + (size_t)pr * nqp + q12 * nq0;
             for (int q0 = 0; q0 < nq0; q0++) acc += pp[q0 * n0 * n0] * dq[q0];
