@@ -17,6 +17,7 @@
 //   fixed column -> zero, its unfixed entry times the value is subtracted from the row's rhs
 //   loads        -> rhs += value * sum over the face elements of BoundaryArea (petigaelem.c:1118-1131)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "pc_plan.h"
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   const int lr0 = lw0 * ((Aj - kp.ls[1]) + kp.lw[1] * (Ak - kp.ls[2]));
   const bool simple_jk = kp.simp[1][gj] && kp.simp[2][gk];
   const int* __restrict__ simple0 = kp.simp[0];
-  const bool fast_ok = (DOF == 1) && simple_jk && !(rsmask0 & 6) && want_mat;
+  const bool fast_ok = (DOF == 1) && !(rsmask0 & 6) && want_mat;
   // right-hand side of an unconstrained row when the load is a single separable term (Poisson, mass)
   const bool vsimple = want_vec && DOF == 1 && kp.nvterms == 1;
   const double vjk = vsimple ? kp.vterms[0].c * kp.mv[1][kp.vterms[0].r1 * kp.nnp[1] + Aj] * kp.mv[2][kp.vterms[0].r2 * kp.nnp[2] + Ak] : 0.0;
@@ -201,13 +202,27 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
     const int lr = il + lr0;
     const int64_t base = __ldg(rowbase + lr);
     const bool SIMPLE = simple_jk && __ldg(simple0 + gi);
-    if (fast_ok && SIMPLE) {
+    if (fast_ok) {
       const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
       if (!rowb && !colb) {
         // interior row: out[cjk*Wi + ci] = M00_i[ci]*G0[cjk] + M11_i[ci]*G3[cjk]; lane = (ci, group), groups stride cjk
         constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC;
-        if (PF > 0 && Wi == WIC && Wjk == WJKC) {   // full-width row of an interior pencil: everything but (a0, a3, base) is static
+        if (!SIMPLE) {   // columns owned by several ranks / periodic wrap: same values, closed-form position per entry
+          const unsigned inv = (65536u + Wi - 1) / Wi;
+          const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
+          if (grp < ngrp) {
+            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
+            const uint32_t s0 = __ldg(kp.seg[0] + gi * kMaxW + ci);
+            const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
+            double* __restrict__ rowp = values + base;
+            for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+              const int info = jkinfo[cjk];
+              const int pos = jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li;
+              rowp[pos] = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+            }
+          }
+        } else if (PF > 0 && Wi == WIC && Wjk == WJKC) {   // full-width row of an interior pencil: everything but (a0, a3, base) is static
           if (grpF < NGRP) {
             const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ciF), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ciF);
             double* __restrict__ rowp = values + base + offF;
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
         }
         continue;
       }
-      if (!kp.fixtable) {
+      if (!kp.fixtable && SIMPLE) {
         // boundary rows of the scalar case (constant Dirichlet values)
         const int rci0 = bcode(Ai, nnp0, per0);
         bool rf[1]; double rv[1];
@@ -585,7 +600,8 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
         if (!L.ax[d].periodic && (fs.vcount || fs.lcount)) kp.any_bc = 1;
       }
   const int blocks = L.ax[1].lw * L.ax[2].lw;
-  const int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
+  int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
+  if (const char* e = getenv("PETIGA_KRON_THREADS")) threads = std::max(32, std::min(256, atoi(e) / 32 * 32));   // tuning knob
   int pf = L.ax[0].p;
   for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
   if (L.dim < 3 || L.dof != 1) pf = 0;
