@@ -222,6 +222,7 @@ int petiga_cuda_set_geometry(petiga_cuda_plan* P, int nsd, const double* X, cons
   PC_CUDA(cudaStreamSynchronize(P->stream));
   cudaFree(P->d_X); cudaFree(P->d_W);
   P->d_X = P->d_W = nullptr;
+  P->config_version++;
   if (!X) return 0;
   if (nsd != P->L.dim) { set_error("geometry: nsd must equal dim on the device path (manifolds unsupported)"); return PETIGA_CUDA_ERR_SUP; }
   const size_t ng = P->L.localrow.size();
@@ -241,6 +242,7 @@ int petiga_cuda_set_bc(petiga_cuda_plan* P, const petiga_cuda_bc* bc) {
   cudaFree(P->d_fixtable);
   P->d_fixtable = nullptr;
   P->has_bc = false;
+  P->config_version++;
   memset(&P->bc, 0, sizeof(P->bc));
   if (!bc) return 0;
   for (int d = 0; d < 3; d++)
@@ -266,6 +268,7 @@ int petiga_cuda_form_select(petiga_cuda_plan* P, int slot, int form_id, const do
   FormInfo fi = form_info(form_id, slot, P->L.dim, P->L.dof);
   if (!fi.valid) { set_error("form_select: this built-in form does not provide that slot for this dim/dof (PETSC_ERR_SUP)"); return PETIGA_CUDA_ERR_SUP; }
   P->slots[slot].form = form_id;
+  P->config_version++;
   memset(P->slots[slot].prm, 0, sizeof(P->slots[slot].prm));
   for (int k = 0; k < nparams; k++) P->slots[slot].prm[k] = params[k];
   return 0;

@@ -526,6 +526,22 @@ void host_terms(int form, int slot, const double* prm, const FormInfo& fi, KronP
 
 }  // namespace
 
+static int launch_kron_kernel(petiga_cuda_plan* P, const KronParams& kp) {
+  const Layout& L = P->L;
+  const int blocks = L.ax[1].lw * L.ax[2].lw;
+  int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
+  if (const char* e = getenv("PETIGA_KRON_THREADS")) threads = std::max(32, std::min(256, atoi(e) / 32 * 32));   // tuning knob
+  int pf = L.ax[0].p;
+  for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
+  if (L.dim < 3 || L.dof != 1) pf = 0;
+#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) kron_rows_kernel<DOF_, PF_><<<blocks, threads, 0, P->stream>>>(kp);
+  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0)
+#undef KL
+  PC_CUDA(cudaGetLastError());
+  P->launches++;
+  return 0;
+}
+
 bool kron_applicable(const petiga_cuda_plan* P, int slot, int form) {
   const Layout& L = P->L;
   if (slot != PETIGA_SLOT_VECTOR && slot != PETIGA_SLOT_MATRIX && slot != PETIGA_SLOT_SYSTEM) return false;
@@ -564,6 +580,15 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
       P->launches++;
     }
   }
+  // the parameter block only depends on (slot, form, parameters, block layout, boundary conditions): build it once and
+  // reuse it, so that a repeated assembly costs one kernel launch on the host side
+  if (P->kron_cache.size() == sizeof(KronParams) && P->kron_cache_slot == slot && P->kron_cache_block == block &&
+      P->kron_cache_version == P->config_version) {
+    KronParams kc;
+    memcpy(&kc, P->kron_cache.data(), sizeof(kc));
+    kc.values = values; kc.rhs = rhs;
+    return launch_kron_kernel(P, kc);
+  }
   KronParams kp;
   memset(&kp, 0, sizeof(kp));
   bool simple = (L.nranks == 1);
@@ -599,18 +624,10 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
         }
         if (!L.ax[d].periodic && (fs.vcount || fs.lcount)) kp.any_bc = 1;
       }
-  const int blocks = L.ax[1].lw * L.ax[2].lw;
-  int threads = std::min(256, std::max(32, ((L.ax[0].lw + 0) * 32)));
-  if (const char* e = getenv("PETIGA_KRON_THREADS")) threads = std::max(32, std::min(256, atoi(e) / 32 * 32));   // tuning knob
-  int pf = L.ax[0].p;
-  for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
-  if (L.dim < 3 || L.dof != 1) pf = 0;
-#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) kron_rows_kernel<DOF_, PF_><<<blocks, threads, 0, P->stream>>>(kp);
-  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0)
-#undef KL
-  PC_CUDA(cudaGetLastError());
-  P->launches++;
-  return 0;
+  P->kron_cache.resize(sizeof(KronParams));
+  memcpy(P->kron_cache.data(), &kp, sizeof(kp));
+  P->kron_cache_slot = slot; P->kron_cache_block = block; P->kron_cache_version = P->config_version;
+  return launch_kron_kernel(P, kp);
 }
 
 }  // namespace pc

@@ -63,6 +63,9 @@ struct petiga_cuda_plan {
   struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
   int path = PETIGA_PATH_AUTO;
   int scatter = 0;
+  std::vector<unsigned char> kron_cache;   // cached parameter block of the separable path
+  int kron_cache_slot = -1, kron_cache_block = -1;
+  long kron_cache_version = -1, config_version = 0;   // bumped by form_select / set_bc / set_geometry
   int quad_impl = -1;             // -1 = choose by element size, 0 = sum-factorised kernel, 1 = pair-loop kernel
   // stats
   long launches = 0;
