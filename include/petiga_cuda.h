@@ -112,6 +112,10 @@ const char *petiga_cuda_strerror(int code);
 const char *petiga_cuda_last_error(void);             /* detail of the last failure on this thread          */
 int         petiga_cuda_device_count(int *count);
 
+/* Measured FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark: best single launch = burst, back-to-back
+   launches for `seconds` = sustained).  The roofline denominator of the quadrature kernels. */
+int         petiga_cuda_measure_fp64(int device, double seconds, double *tflops_burst, double *tflops_sustained);
+
 /* ---- plan ---- */
 /* stream: a cudaStream_t (NULL = the plan creates its own non-blocking stream).
    nccl_comm: an ncclComm_t spanning `nranks` ranks, or NULL when nranks == 1 (or to let the plan use

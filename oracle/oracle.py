@@ -14,6 +14,7 @@ _LIB = None
 
 SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6)
 FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7)
+SCALAR = dict(ERRNORM=0, CH_STATS=1)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -78,6 +79,7 @@ def lib(native=False):
                                 C.c_void_p, _dp, _dp]
     L.oiga_assemble_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
                                      C.c_void_p, _dp, _dp]
+    L.oiga_compute_scalar.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
     L.oiga_tabulate_element.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 12
     if not native:
         _LIB = L
@@ -207,6 +209,20 @@ class OracleIGA:
         rc = self.L.oiga_assemble(self.h, size, slot_i, FORM[form], _d(prm), shift, _d(Vc), t, _d(Uc), p, _d(vals), _d(rhs))
         assert rc == 0, "oracle assemble failed rc=%d" % rc
         return vals, rhs
+
+    def compute_scalar(self, scalar, params, n, U=None, size=1):
+        """IGAComputeScalar (src/petigacomp.c:35-96) with a built-in Scalar callback: 'ERRNORM' (ErrorSqr :103-124,
+        params = [k, exact id, choice]) or 'CH_STATS' (demo/CahnHilliard2D.c:43-58, params = [theta, alpha, cbar])."""
+        prm = np.ascontiguousarray(list(params) + [0.0] * 4, dtype=np.float64)
+        Uc = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
+        S = np.zeros(n)
+        rc = self.L.oiga_compute_scalar(self.h, size, SCALAR[scalar], _d(prm), _d(Uc), n, _d(S))
+        assert rc == 0, "oracle compute_scalar failed rc=%d" % rc
+        return S
+
+    def error_norm(self, k, U=None, exact=1, choice=0, size=1):
+        """IGAComputeErrorNorm (src/petigacomp.c:155-186)."""
+        return np.sqrt(self.compute_scalar("ERRNORM", [k, exact, choice], self.dof, U=U, size=size))
 
     def tabulate(self, ID, order=3):
         inf = self.info()

@@ -1324,6 +1324,105 @@ int oiga_assemble_rank(OIGA *o, int size, int rank, int slot, int form, const do
                        double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
 { return assemble(o, size, rank, rank+1, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
 
+/* ------------------------------------------------------------------------------------------ */
+/* IGAComputeScalar / IGAComputeErrorNorm: src/petigacomp.c:35-186                              */
+/* ------------------------------------------------------------------------------------------ */
+enum { SCALAR_ERRNORM=0, SCALAR_CH_STATS=1 };
+
+/* IGAPointEvaluate (petigapoint.c:387-412) -> IGA_GetValue/Grad/Hess (petigaval.F90:182-232): V(dim^k,dof) */
+static void point_evaluate(const Point *p, int k, const double *U, double *u)
+{
+  int a, i, c, n = ipow(p->dim, k);
+  const double *N = (k == 0) ? p->N0 : (k == 1) ? p->N1 : p->N2;
+  for (c = 0; c < p->dof*n; c++) u[c] = 0;
+  for (a = 0; a < p->nen; a++) for (i = 0; i < p->dof; i++) for (c = 0; c < n; c++)
+    u[i*n+c] = u[i*n+c] + N[(size_t)a*n+c] * U[a*p->dof+i];
+}
+
+/* exact solutions usable as the Exact callback.  id 1: test/IGAErrNorm.c:26-52 (dof 4: 1, sum x, sum x^2, prod x);
+   id 2: demo/L2Projection.c:3-61 value only (choice = prm2), same function for every field */
+static int exact_eval(int id, int choice, int dim, int dof, const double *x, int k, double *value)
+{
+  int i, j, c, n = ipow(dim, k);
+  if (id == 1) {
+    double prod = 1; for (i = 0; i < dim; i++) prod *= x[i];
+    if (dof != 4 || k > 2) return 1;
+    if (k == 0) { double s1 = 0, s2 = 0; for (i = 0; i < dim; i++) { s1 += x[i]; s2 += x[i]*x[i]; }
+      value[0] = 1; value[1] = s1; value[2] = s2; value[3] = prod; }
+    else if (k == 1) { for (i = 0; i < dim; i++) { value[0*dim+i] = 0; value[1*dim+i] = 1; value[2*dim+i] = 2*x[i]; value[3*dim+i] = prod/x[i]; } }
+    else { for (i = 0; i < dim; i++) for (j = 0; j < dim; j++) { value[0*n+i*dim+j] = 0; value[1*n+i*dim+j] = 0;
+      value[2*n+i*dim+j] = (i==j) ? 2 : 0; value[3*n+i*dim+j] = (i==j) ? 0 : (prod/(x[i]*x[j])); } }
+    return 0;
+  }
+  if (id == 2) { double xx[3] = {0,0,0}; if (k != 0) return 1; for (i = 0; i < dim; i++) xx[i] = x[i];
+    for (c = 0; c < dof; c++) value[c] = l2_function(choice, dim, xx); return 0; }
+  return 1;
+}
+
+/* the Scalar callbacks: ErrorSqr (petigacomp.c:103-124) and the CahnHilliard monitor Stats (demo/CahnHilliard2D.c:36-58) */
+static int scalar_point(int sid, const double *prm, const Point *p, const double *U, int n, double *S, double *w0, double *w1)
+{
+  int i, j;
+  if (sid == SCALAR_ERRNORM) {
+    int k = (int)prm[0], ex = (int)prm[1], nn = ipow(p->dim, k);
+    if (k < 0 || k > 2 || n != p->dof) return 1;
+    if (U) point_evaluate(p, k, U, w0); else for (i = 0; i < p->dof*nn; i++) w0[i] = 0;   /* vecU == NULL: zero state */
+    for (i = 0; i < p->dof*nn; i++) w1[i] = 0;
+    if (ex) { if (exact_eval(ex, (int)prm[2], p->dim, p->dof, p->x, k, w1)) return 1; }
+    for (i = 0; i < p->dof; i++) for (j = 0; j < nn; j++) { double e = fabs(w1[i*nn+j] - w0[i*nn+j]); S[i] += e*e; }
+    return 0;
+  }
+  if (sid == SCALAR_CH_STATS) {
+    double theta = prm[0], alpha = prm[1], cbar = prm[2], c, c1[3], diff;
+    if (p->dim != 2 || p->dof != 1 || n != 3 || !U) return 1;
+    get_value(p, U, &c); get_grad(p, U, c1);
+    diff = c - cbar;
+    S[0] = c*log(c) + (1-c)*log(1-c) + 2*theta*c*(1-c) + theta/(3*alpha)*(c1[0]*c1[0]+c1[1]*c1[1]);
+    S[1] = diff*diff;
+    S[2] = S[1]*diff;
+    return 0;
+  }
+  return 1;
+}
+
+/* IGAComputeScalar (petigacomp.c:35-96) over `size` emulated ranks; the final loop over ranks is the MPI_Allreduce */
+int oiga_compute_scalar(OIGA *o, int size, int sid, const double *prm, const double *Ug, int n, double *S)
+{
+  int r, err = 0, i;
+  double *localS = (double*)calloc((size_t)n*size, sizeof(double)), *workS = (double*)malloc(sizeof(double)*(size_t)n);
+  for (r = 0; r < size && !err; r++) {
+    Elem e; int index, count, N, ng, dof = o->dof; double *U = NULL, *arrayU = NULL, *w0, *w1;
+    if (setup_rank(o, size, r)) { err = 1; break; }
+    elem_alloc(&e, o);
+    N = e.nen*dof; ng = o->node_gwidth[0]*o->node_gwidth[1]*o->node_gwidth[2];
+    w0 = (double*)malloc(sizeof(double)*(size_t)dof*81); w1 = (double*)malloc(sizeof(double)*(size_t)dof*81);
+    if (Ug) { int a, c; U = (double*)malloc(sizeof(double)*(size_t)N); arrayU = (double*)malloc(sizeof(double)*(size_t)ng*dof);
+      for (a = 0; a < ng; a++) for (c = 0; c < dof; c++) arrayU[(size_t)a*dof+c] = Ug[(size_t)o->lgmap[a]*dof+c]; }
+    count = o->elem_width[0]*o->elem_width[1]*o->elem_width[2];
+    for (index = 0; index < count && !err; index++) {
+      int q, a, idx = index;
+      for (i = 0; i < 3; i++) { int coord = idx % o->elem_width[i]; idx = (idx - coord)/o->elem_width[i]; e.ID[i] = coord + o->elem_start[i]; }
+      elem_closure(&e);
+      if (Ug) for (a = 0; a < e.nen; a++) for (i = 0; i < dof; i++) U[a*dof+i] = arrayU[(size_t)e.mapping[a]*dof+i];   /* IGAElementGetValues */
+      elem_tabulate(&e);
+      for (q = 0; q < e.nqp; q++) {
+        Point p; double JW = e.detJac[q] * e.weight[q];
+        p.nen = e.nen; p.dof = dof; p.dim = e.dim; p.nsd = e.nsd;
+        p.N0 = e.shape[0] + (size_t)q*e.nen; p.N1 = e.shape[1] + (size_t)q*e.nen*e.nsd; p.N2 = e.shape[2] + (size_t)q*e.nen*e.nsd*e.nsd;
+        p.x = e.geometry ? e.mapX[0] + (size_t)q*e.nsd : e.mapU[0] + (size_t)q*e.dim;
+        memset(workS, 0, sizeof(double)*(size_t)n);
+        if (scalar_point(sid, prm, &p, U, n, workS, w0, w1)) { err = 10; break; }
+        for (i = 0; i < n; i++) localS[(size_t)r*n+i] += workS[i] * JW;    /* IGAPointAddArray (petigapoint.c:451-465) */
+      }
+    }
+    free(U); free(arrayU); free(w0); free(w1);
+    elem_free(&e);
+  }
+  for (i = 0; i < n; i++) { S[i] = 0; for (r = 0; r < size; r++) S[i] += localS[(size_t)r*n+i]; }
+  free(localS); free(workS);
+  return err;
+}
+
 /* Tabulate one element of the current rank (after oiga_setup) for the geometry known-answer tests.
    out arrays sized by the caller: weight[nqp], detJac[nqp] (already *detX), detX[nqp], point[nqp][dim],
    X0[nqp][nsd], X1[nqp][nsd][dim], shape0[nqp][nen], shape1[nqp][nen][nsd], shape2[nqp][nen][nsd][nsd] */

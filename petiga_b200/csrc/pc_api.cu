@@ -1,4 +1,5 @@
 // pc_api.cu -- extern "C" entry points of libpetiga_cuda (see include/petiga_cuda.h).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -71,6 +72,21 @@ __global__ void pattern_kernel(const __grid_constant__ PatParams pp) {
 
 __global__ void gather_owned_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// FP64 FMA peak: 8 independent DFMA chains per thread, 4 CTAs of 256 threads per SM (the roofline denominator of the
+// quadrature kernels; MEASURED_PEAKS.json carries no FP64 figure, SURVEY 8d asks for a measured one)
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;   // never true for the arguments used; keeps the chains alive
 }
 
 }  // namespace pc
@@ -488,6 +504,46 @@ int petiga_cuda_compute_host(petiga_cuda_plan* P, int slot, int block, double sh
   if (values_host) PC_CUDA(cudaMemcpyAsync(values_host, P->d_values_own, nval * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
   if (rhs_host) PC_CUDA(cudaMemcpyAsync(rhs_host, P->d_rhs_own, nvec * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
   return petiga_cuda_finish(P);
+}
+
+// ---- measured FP64 FMA peak of the device (roofline denominator for the quadrature kernels) ----
+int petiga_cuda_measure_fp64(int device, double seconds, double* tflops_burst, double* tflops_sustained) {
+  int ndev = 0;
+  int rc = petiga_cuda_device_count(&ndev);
+  if (rc) return rc;
+  if (device < 0 || device >= ndev) return PETIGA_CUDA_ERR_ARG;
+  PC_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  PC_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms * 4, iters = 4096;
+  const double flop = 2.0 * 64.0 * iters * 256.0 * blocks;      // 64 DFMA per iteration per thread
+  double best = 0.0, sus_flop = 0.0;
+  float ms = 0.f;
+  for (int it = 0; it < 12; it++) {   // burst: best single launch (~1 ms each)
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    PC_CUDA(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it >= 2 && ms > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  // sustained: back-to-back launches for `seconds`
+  const int nl = std::max(1, (int)(seconds * 1e3 / std::max(0.05, flop / (best * 1e12) * 1e3)));
+  cudaEventRecord(e0);
+  for (int it = 0; it < nl; it++) { dfma_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9); sus_flop += flop; }
+  cudaEventRecord(e1);
+  PC_CUDA(cudaEventSynchronize(e1));
+  cudaEventElapsedTime(&ms, e0, e1);
+  PC_CUDA(cudaGetLastError());
+  if (tflops_burst) *tflops_burst = best;
+  if (tflops_sustained) *tflops_sustained = sus_flop / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return 0;
 }
 
 // ---- small device-memory helpers ----

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
+  __shared__ double jkval[kMaxWW];               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
   __shared__ double stage[(DOF > 1) ? 8 * 32 * DOF * DOF : 1];
   const int Aj = kp.ls[1] + (int)(blockIdx.x % kp.lw[1]), Ak = kp.ls[2] + (int)(blockIdx.x / kp.lw[1]);
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
@@ -166,6 +167,11 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
       p1 = Bk * Wj + Sk * Bj;
       info |= (Sk * Sj) << 8;
       info |= (Lk * Sj + Lj) << 16;
+    }
+    if (DOF == 1 && fixing && (info & 15)) {   // "last face wins": k over j over i (AddFixa overwrites, petigaelem.c:1166-1189)
+      bool f[1]; double fv[1];
+      node_fix<1>(kp, 0, info & 3, (info >> 2) & 3, f, fv);
+      if (f[0]) { info |= 32; jkval[t] = fv[0]; }
     }
     jkinfo[t] = info;
     jkp1[t] = p1;
@@ -269,8 +275,9 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
         }
         continue;
       }
-      if (!kp.fixtable && SIMPLE) {
-        // boundary rows of the scalar case (constant Dirichlet values)
+      if (!kp.fixtable) {
+        // boundary rows of the scalar case (constant Dirichlet values): column fix data is per-lane (axis 0) and
+        // per-cjk (shared memory), so an entry costs a flag test instead of a walk over the face tables
         const int rci0 = bcode(Ai, nnp0, per0);
         bool rf[1]; double rv[1];
         node_fix<1>(kp, rci0, rcj, rck, rf, rv);
@@ -279,7 +286,13 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
         double racc0 = 0.0;
         if (rowb && rf[0]) {
           // fixed row: zero except the diagonal, which counts the elements containing the node (petigaelem.c:1377-1387)
-          const int ediag = ((Ak - fk) * Wj + (Aj - fj)) * Wi + (Ai - fi);
+          const int cjkd = (Ak - fk) * Wj + (Aj - fj), cid = Ai - fi;
+          int ediag = cjkd * Wi + cid;
+          if (!SIMPLE) {
+            const uint32_t s0 = __ldg(kp.seg[0] + gi * kMaxW + cid);
+            const int info = jkinfo[cjkd];
+            ediag = jkp1[cjkd] * Wi + ((info >> 8) & 255) * (int)(s0 & 255) + ((info >> 16) & 255) * (int)((s0 >> 8) & 255) + (int)((s0 >> 16) & 255);
+          }
           for (int e = lane; e < W; e += 32) rowp[e] = (e == ediag) ? nel : 0.0;
           if (want_vec && lane == 0) rhs[lr] = nel * rv[0];
           continue;
@@ -289,29 +302,41 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
           const int grp = (int)((lane * inv) >> 16), ci = lane - grp * Wi, ngrp = (int)((32u * inv) >> 16);
           if (grp < ngrp) {
             const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ci), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ci);
-            const int cci = bcode(fi + ci, nnp0, per0);
-            double* out = rowp + grp * Wi + ci;
-            const int ostep = ngrp * Wi;
-            for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
-              double v = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
-              const int info = jkinfo[cjk];
-              if (cci | (info & 15)) {
-                bool cf[1]; double cv[1];
-                node_fix<1>(kp, cci, info & 3, (info >> 2) & 3, cf, cv);
-                if (cf[0]) { racc0 -= v * cv[0]; v = 0.0; }
+            bool cfi[1]; double cvi[1];
+            node_fix<1>(kp, bcode(fi + ci, nnp0, per0), 0, 0, cfi, cvi);
+            const bool ifix = cfi[0];
+            const double ival = cvi[0];
+            if (SIMPLE) {
+              double* out = rowp + grp * Wi + ci;
+              const int ostep = ngrp * Wi;
+              for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+                double v = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+                if (jkinfo[cjk] & 32) { racc0 = fma(-v, jkval[cjk], racc0); v = 0.0; }
+                else if (ifix) { racc0 = fma(-v, ival, racc0); v = 0.0; }
+                *out = v;
+                out += ostep;
               }
-              *out = v;
-              out += ostep;
+            } else {
+              const uint32_t s0 = __ldg(kp.seg[0] + gi * kMaxW + ci);
+              const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
+              for (int cjk = grp; cjk < Wjk; cjk += ngrp) {
+                double v = fma(a3, G[3][0][cjk], a0 * G[0][0][cjk]);
+                const int info = jkinfo[cjk];
+                if (info & 32) { racc0 = fma(-v, jkval[cjk], racc0); v = 0.0; }
+                else if (ifix) { racc0 = fma(-v, ival, racc0); v = 0.0; }
+                rowp[jkp1[cjk] * Wi + ((info >> 8) & 255) * Bi + ((info >> 16) & 255) * Si + Li] = v;
+              }
             }
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) racc0 += __shfl_xor_sync(0xffffffffu, racc0, o);
           if (want_vec && lane == 0) {
-            double F = 0.0;
-            for (int n = 0; n < kp.nvterms; n++) {
-              const KronVTerm vt = kp.vterms[n];
-              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
-            }
+            double F = vsimple ? vjk * __ldg(mv0 + Ai) : 0.0;
+            if (!vsimple)
+              for (int n = 0; n < kp.nvterms; n++) {
+                const KronVTerm vt = kp.vterms[n];
+                F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+              }
             if (rowb) {   // loads on the faces this (unfixed) node lies on
               const int rcode[3] = {rci0, rcj, rck};
               for (int d = 0; d < kp.dim; d++) {
