@@ -73,6 +73,16 @@ enum {
   PETIGA_NFORMS = 8
 };
 
+/* built-in Scalar callbacks of petiga_cuda_compute_scalar (IGAComputeScalar, src/petigacomp.c:35-96) */
+enum {
+  PETIGA_SCALAR_ERRNORM = 0,      /* ErrorSqr of IGAComputeErrorNorm (src/petigacomp.c:103-124): n = dof squared errors;
+                                     params = {k (0..2), exact id, choice}; exact id 0 = NULL, 1 = test/IGAErrNorm.c:26-52
+                                     (dof 4), 2 = demo/L2Projection.c:3-61 function `choice` (k = 0)                      */
+  PETIGA_SCALAR_CH_STATS = 1,     /* demo/CahnHilliard2D.c:36-58 monitor: n = 3 (free energy, 2nd, 3rd moment);
+                                     params = {theta, alpha, cbar}                                                          */
+  PETIGA_NSCALARS = 2
+};
+
 /* assembly algorithm selection (petiga_cuda_set_option "path") */
 enum {
   PETIGA_PATH_AUTO = 0,           /* Kronecker row-gather when the form/geometry is separable, else quadrature     */
@@ -152,6 +162,13 @@ int petiga_cuda_plan_lgmap_host(petiga_cuda_plan *plan, int *lgmap);   /* ghost 
 int petiga_cuda_compute(petiga_cuda_plan *plan, int slot, int block, double shift, const double *V, double t,
                         const double *U, double *values, double *rhs);
 int petiga_cuda_finish(petiga_cuda_plan *plan);
+
+/* IGAComputeScalar (src/petigacomp.c:35-96): S[k] = sum over all ranks, elements and quadrature points of
+   detJac*weight * Scalar_k(point, U).  U: device [owned nodes * dof] or NULL (a NULL state evaluates as zero, which is how
+   IGAComputeErrorNorm(iga,k,NULL,Exact,..) yields the norms of the exact solution).  S_host receives the n global sums on
+   every rank (the reference's MPI_Allreduce); the call synchronises the plan's stream.  Sums are deterministic. */
+int petiga_cuda_compute_scalar(petiga_cuda_plan *plan, int scalar_id, const double *params, int nparams,
+                               const double *U, int n, double *S_host);
 
 /* host-buffer convenience (the end-to-end call: H2D of U/V, compute, D2H of values/rhs, synchronous) */
 int petiga_cuda_compute_host(petiga_cuda_plan *plan, int slot, int block, double shift, const double *V_host,

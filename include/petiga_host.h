@@ -62,6 +62,9 @@ typedef PetscErrorCode (*IGAFormJacobian)(IGAPoint p, const PetscScalar *U, Pets
 typedef PetscErrorCode (*IGAFormIFunction)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *F, void *ctx);
 typedef PetscErrorCode (*IGAFormIJacobian)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *J, void *ctx);
 
+typedef PetscErrorCode (*IGAFormScalar)(IGAPoint p, const PetscScalar *U, PetscInt n, PetscScalar *S, void *ctx);   /* petiga.h:172 */
+typedef PetscErrorCode (*IGAFormExact)(IGAPoint p, PetscInt k, PetscScalar V[], void *ctx);                          /* petiga.h:173 */
+
 /* ---- device-form sentinels: pass these where the reference passes the demo's callback; ctx points at the
         demo's AppCtx (its leading PetscReal members are the parameters).  Calling them on the host fails. ---- */
 PetscErrorCode IGADeviceForm_Poisson_System(IGAPoint, PetscScalar *, PetscScalar *, void *);            /* demo/Poisson{1,2,3}D.c System      */
@@ -80,6 +83,11 @@ PetscErrorCode IGADeviceForm_Bratu_Function(IGAPoint, const PetscScalar *, Petsc
 PetscErrorCode IGADeviceForm_Bratu_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_IFunction(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_IJacobian(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+
+/* Scalar / Exact sentinels for IGAComputeScalar and IGAComputeErrorNorm (src/petigacomp.c:35-186) */
+PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar *, PetscInt, PetscScalar *, void *);  /* demo/CahnHilliard2D.c:43-58; ctx: {theta, alpha, cbar} */
+PetscErrorCode IGADeviceExact_ErrNormTest(IGAPoint, PetscInt, PetscScalar *, void *);     /* test/IGAErrNorm.c:26-52 (dof 4: 1, sum x, sum x^2, prod x) */
+PetscErrorCode IGADeviceExact_L2Projection(IGAPoint, PetscInt, PetscScalar *, void *);    /* demo/L2Projection.c:3-61; ctx: {PetscReal choice}; k = 0     */
 
 /* ---- IGA object: include/petiga.h:393-460 ---- */
 PetscErrorCode IGACreate(IGAComm comm, IGA *iga);
@@ -139,6 +147,11 @@ PetscErrorCode IGAComputeFunction(IGA iga, Vec U, Vec F);
 PetscErrorCode IGAComputeJacobian(IGA iga, Vec U, Mat J);
 PetscErrorCode IGAComputeIFunction(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Vec F);
 PetscErrorCode IGAComputeIJacobian(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Mat J);
+
+/* ---- functionals: src/petigacomp.c:35-186.  vecU may be NULL; Scalar/Exact must be one of the sentinels above
+        (Exact may be NULL: norms of the discrete field) ---- */
+PetscErrorCode IGAComputeScalar(IGA iga, Vec vecU, PetscInt n, PetscScalar S[], IGAFormScalar Scalar, void *ctx);
+PetscErrorCode IGAComputeErrorNorm(IGA iga, PetscInt k, Vec vecU, IGAFormExact Exact, PetscReal enorm[], void *ctx);
 
 /* ---- introspection used by the tests / bench ---- */
 PetscErrorCode IGAGetInfoArray(IGA iga, PetscInt info[46]);     /* same layout as the oracle's oiga_get_info */

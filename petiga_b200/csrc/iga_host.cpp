@@ -306,6 +306,9 @@ SENT4(IGADeviceForm_Laplace_System) SENT4(IGADeviceForm_L2Projection_System) SEN
 SENT3(IGADeviceForm_Mass_Matrix) SENT3(IGADeviceForm_Mass_Vector)
 SENT4(IGADeviceForm_Elasticity3D_System) SENT4(IGADeviceForm_Elasticity_System)
 SENTI(IGADeviceForm_CahnHilliard2D_Residual) SENTI(IGADeviceForm_CahnHilliard2D_Tangent)
+PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar*, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
+PetscErrorCode IGADeviceExact_ErrNormTest(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
+PetscErrorCode IGADeviceExact_L2Projection(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 SENTF(IGADeviceForm_Bratu_Function) SENTF(IGADeviceForm_Bratu_Jacobian) SENTI(IGADeviceForm_Bratu_IFunction) SENTI(IGADeviceForm_Bratu_IJacobian)
 
 PetscErrorCode IGA_Partition(PetscInt size, PetscInt rank, PetscInt dim, const PetscInt N[], PetscInt n[], PetscInt i[]) {
@@ -656,6 +659,36 @@ PetscErrorCode IGAComputeFunction(IGA g, Vec U, Vec F) { if (!U || !F) return fa
 PetscErrorCode IGAComputeJacobian(IGA g, Vec U, Mat J) { if (!U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_JACOBIAN, 0, nullptr, 0, U, J, nullptr); }
 PetscErrorCode IGAComputeIFunction(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, Vec F) { if (!V || !U || !F) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_IFUNCTION, a, V, t, U, nullptr, F); }
 PetscErrorCode IGAComputeIJacobian(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, Mat J) { if (!V || !U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_IJACOBIAN, a, V, t, U, J, nullptr); }
+
+// src/petigacomp.c:35-96
+PetscErrorCode IGAComputeScalar(IGA g, Vec vecU, PetscInt n, PetscScalar S[], IGAFormScalar Scalar, void* ctx) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!S) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  if (Scalar != IGADeviceScalar_CahnHilliard2D_Stats)
+    return fail(PETSC_ERR_SUP, "IGAComputeScalar: host callbacks cannot run on the GPU; pass one of the IGADeviceScalar_* sentinels");
+  if (!ctx) return fail(PETSC_ERR_ARG_NULL, "IGAComputeScalar: this functional needs its AppCtx");
+  if (PetscErrorCode e = ensure_plan(g)) return e;
+  return from_cuda(petiga_cuda_compute_scalar(g->plan, PETIGA_SCALAR_CH_STATS, (const double*)ctx, 3, vecU ? vecU->d : nullptr, n, S));
+}
+// src/petigacomp.c:155-186
+PetscErrorCode IGAComputeErrorNorm(IGA g, PetscInt k, Vec vecU, IGAFormExact Exact, PetscReal enorm[], void* ctx) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!enorm) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  if (k < 0) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Derivative index must be nonnegative");   // :170
+  double prm[3] = {(double)k, 0.0, 0.0};
+  if (Exact == IGADeviceExact_ErrNormTest) prm[1] = 1;
+  else if (Exact == IGADeviceExact_L2Projection) { prm[1] = 2; if (!ctx) return fail(PETSC_ERR_ARG_NULL, "IGADeviceExact_L2Projection needs {choice}"); prm[2] = *(const double*)ctx; }
+  else if (Exact) return fail(PETSC_ERR_SUP, "IGAComputeErrorNorm: host callbacks cannot run on the GPU; pass one of the IGADeviceExact_* sentinels or NULL");
+  if (PetscErrorCode e = ensure_plan(g)) return e;
+  double errsqr[8];
+  if (g->dof > 8) return fail(PETSC_ERR_SUP, "IGAComputeErrorNorm: dof > 8");
+  int rc = petiga_cuda_compute_scalar(g->plan, PETIGA_SCALAR_ERRNORM, prm, 3, vecU ? vecU->d : nullptr, g->dof, errsqr);
+  if (rc) return from_cuda(rc);
+  for (int i = 0; i < g->dof; i++) enorm[i] = sqrt(errsqr[i]);   // :180
+  return 0;
+}
 
 PetscErrorCode IGAGetInfoArray(IGA g, PetscInt info[46]) {
   if (PetscErrorCode e = check(g)) return e;

@@ -20,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -65,7 +66,7 @@ int nccl_load() {
 #define LOADSYM(field, sym) *(void**)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) { set_error("missing NCCL symbol " sym); return PETIGA_CUDA_ERR_NCCL; }
   LOADSYM(GetUniqueId, "ncclGetUniqueId") LOADSYM(CommInitRank, "ncclCommInitRank") LOADSYM(CommDestroy, "ncclCommDestroy")
   LOADSYM(Send, "ncclSend") LOADSYM(Recv, "ncclRecv") LOADSYM(GroupStart, "ncclGroupStart") LOADSYM(GroupEnd, "ncclGroupEnd")
-  LOADSYM(GetErrorString, "ncclGetErrorString")
+  LOADSYM(GetErrorString, "ncclGetErrorString") LOADSYM(AllReduce, "ncclAllReduce")
 #undef LOADSYM
   g_nccl.handle = h;
   return 0;
@@ -77,6 +78,16 @@ static int ensure_recv(petiga_cuda_plan* P, size_t n) {
   P->d_recv = nullptr; P->recv_cap = 0;
   PC_CUDA(cudaMalloc(&P->d_recv, (n ? n : 1) * sizeof(double)));
   P->recv_cap = n;
+  return 0;
+}
+
+// MPI_Allreduce(SUM) of IGAComputeScalar (src/petigacomp.c:90), in place on the plan's stream
+int allreduce_sum(petiga_cuda_plan* P, double* d_buf, int n) {
+  if (!P->nccl) { set_error("multi-rank plan without an NCCL communicator"); return PETIGA_CUDA_ERR_ORDER; }
+  int rc = nccl_load();
+  if (rc) return rc;
+  PC_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)P->nccl, P->stream));
+  P->launches += 1;
   return 0;
 }
 

@@ -49,6 +49,7 @@ struct KronParams {
   int gw[3];
   int dim, dof, block, slot, simple, wfull0;
   int nterms, nvterms, rsmask0;
+  int fast_lo, fast_hi;   // axis-0 local row range [lo,hi) of full-width, storage-ordered, unconstrained rows (multiple of 4 long)
   int rsmask_ij[9];       // per (i,j) block: which axis-0 order pairs occur
   KronTerm terms[kMaxTerms];
   KronVTerm vterms[8];
@@ -135,7 +136,7 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 // row in storage order, so every store instruction writes 256 contiguous bytes.
 // PF > 0: all axes have degree PF, so a full-width interior row has compile-time extents and its loop unrolls completely
 template <int DOF, int PF>
-__global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ KronParams kp) {
+__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(const __grid_constant__ KronParams kp) {
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
@@ -202,12 +203,73 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
   // full-width rows (W_i = 2p+1, all but the first/last p rows of a pencil): lane -> (column offset, group) fixed per warp
   const int WiF = kp.wfull0, ngrpF = 32 / WiF, grpF = lane / WiF, ciF = lane - grpF * WiF;
   const int ostepF = ngrpF * WiF, offF = grpF * WiF + ciF, nfullF = Wjk / ngrpF;   // every group runs nfullF full iterations
-  for (int il = warp; il < lw0; il += nwarps) {
+  // ---- interior stretch of an interior pencil: 4 rows per warp pass share the G loads; no per-row tests ----
+  int nfast = 0;
+  const int fast_lo = kp.fast_lo;
+  if (PF > 0) {
+    constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC, RW = WIC * WJKC, R = 4;
+    const bool pencil_fast = fast_ok && simple_jk && !jk_boundary && !(fixing && (rcj || rck)) && Wjk == WJKC && WiF == WIC && kp.fast_hi > fast_lo;
+    if (pencil_fast) {
+      nfast = kp.fast_hi - fast_lo;
+      const int64_t base_lo = __ldg(rowbase + lr0 + fast_lo);
+      for (int il = fast_lo + warp * R; il < kp.fast_hi; il += nwarps * R) {
+        if (grpF < NGRP) {
+          double a0[R], a3[R];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            a0[r] = __ldg(M0 + (size_t)(ls0 + il + r) * kMaxW + ciF);
+            a3[r] = __ldg(M0 + ((size_t)3 * nnp0 + ls0 + il + r) * kMaxW + ciF);
+          }
+          double* __restrict__ rowp = values + base_lo + (int64_t)(il - fast_lo) * RW + offF;
+          const double* __restrict__ g0 = &G[0][0][grpF];
+          const double* __restrict__ g3 = &G[3][0][grpF];
+#pragma unroll
+          for (int k = 0; k < NITER; k++)
+            if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) {
+              const double x0 = g0[k * NGRP], x3 = g3[k * NGRP];
+#pragma unroll
+              for (int r = 0; r < R; r++) rowp[r * RW + k * OSTEP] = fma(a3[r], x3, a0[r] * x0);
+            }
+        }
+        if (want_vec && lane < R) {
+          const int Ai = ls0 + il + lane;
+          double F;
+          if (vsimple) F = vjk * __ldg(mv0 + Ai);
+          else {
+            F = 0.0;
+            for (int n = 0; n < kp.nvterms; n++) {
+              const KronVTerm vt = kp.vterms[n];
+              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+            }
+          }
+          rhs[lr0 + il + lane] = F;
+        }
+      }
+    }
+  }
+  const int nslow = lw0 - nfast;   // the general loop walks the remaining rows (compacted index)
+  // per-row parameters are prefetched one row ahead (registers), so that their L2 latency overlaps the stores of the
+  // current row instead of stalling every row (ncu r1_ncu_kron_rows_mesh128_v3: long_scoreboard was the top stall)
+  struct RowP { int Wi, fi, simple; int64_t base; double a0, a3; };
+  auto load_row = [&](int il_) {
+    RowP r;
+    const int Ai_ = ls0 + il_, gi_ = Ai_ - gs0;
+    r.Wi = __ldg(Wg0 + gi_); r.fi = __ldg(first0 + Ai_); r.simple = __ldg(simple0 + gi_);
+    r.base = __ldg(rowbase + il_ + lr0);
+    r.a0 = __ldg(M0 + (size_t)Ai_ * kMaxW + ciF); r.a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai_) * kMaxW + ciF);
+    return r;
+  };
+  RowP cur = {0, 0, 0, 0, 0.0, 0.0}, nxt = cur;
+  auto row_of = [&](int idx) { return (idx < fast_lo || nfast == 0) ? idx : idx + nfast; };
+  if (warp < nslow) cur = load_row(row_of(warp));
+  for (int idx = warp; idx < nslow; idx += nwarps, cur = nxt) {
+    if (idx + nwarps < nslow) nxt = load_row(row_of(idx + nwarps));
+    const int il = row_of(idx);
     const int Ai = ls0 + il, gi = Ai - gs0;
-    const int Wi = __ldg(Wg0 + gi), fi = __ldg(first0 + Ai), W = Wi * Wjk;
+    const int Wi = cur.Wi, fi = cur.fi, W = Wi * Wjk;
     const int lr = il + lr0;
-    const int64_t base = __ldg(rowbase + lr);
-    const bool SIMPLE = simple_jk && __ldg(simple0 + gi);
+    const int64_t base = cur.base;
+    const bool SIMPLE = simple_jk && cur.simple;
     if (fast_ok) {
       const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
@@ -230,7 +292,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
           }
         } else if (PF > 0 && Wi == WIC && Wjk == WJKC) {   // full-width row of an interior pencil: everything but (a0, a3, base) is static
           if (grpF < NGRP) {
-            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ciF), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ciF);
+            const double a0 = cur.a0, a3 = cur.a3;
             double* __restrict__ rowp = values + base + offF;
             const double* __restrict__ g0 = &G[0][0][grpF];
             const double* __restrict__ g3 = &G[3][0][grpF];
@@ -240,7 +302,7 @@ __global__ void __launch_bounds__(256) kron_rows_kernel(const __grid_constant__ 
           }
         } else if (Wi == WiF) {   // full-width row: lane mapping and trip count hoisted out of the row loop
           if (grpF < ngrpF) {
-            const double a0 = __ldg(M0 + (size_t)Ai * kMaxW + ciF), a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai) * kMaxW + ciF);
+            const double a0 = cur.a0, a3 = cur.a3;
             double* __restrict__ rowp = values + base + offF;
             int cjk = grpF;
             for (int it = 0; it < nfullF; ++it) {
@@ -649,6 +711,23 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
         }
         if (!L.ax[d].periodic && (fs.vcount || fs.lcount)) kp.any_bc = 1;
       }
+  {  // longest run of axis-0 rows that are full-width, in storage order and free of Dirichlet rows/columns
+    const AxisLayout& a0 = L.ax[0];
+    const bool fixing0 = kp.any_bc && slot == PETIGA_SLOT_SYSTEM && !a0.periodic;
+    int best_lo = 0, best_hi = 0, run_lo = -1;
+    for (int il = 0; il <= a0.lw; il++) {
+      bool ok = false;
+      if (il < a0.lw) {
+        const int Ai = a0.ls + il, gi = Ai - a0.gs, Wi = a0.W[gi], fi = a0.first[Ai];
+        ok = (Wi == 2 * a0.p + 1) && a0.simple[gi];
+        if (ok && fixing0 && (Ai == 0 || Ai == a0.nnp - 1 || fi == 0 || fi + Wi == a0.nnp)) ok = false;
+      }
+      if (ok) { if (run_lo < 0) run_lo = il; }
+      else if (run_lo >= 0) { if (il - run_lo > best_hi - best_lo) { best_lo = run_lo; best_hi = il; } run_lo = -1; }
+    }
+    kp.fast_lo = best_lo;
+    kp.fast_hi = best_lo + (best_hi - best_lo) / 4 * 4;
+  }
   P->kron_cache.resize(sizeof(KronParams));
   memcpy(P->kron_cache.data(), &kp, sizeof(kp));
   P->kron_cache_slot = slot; P->kron_cache_block = block; P->kron_cache_version = P->config_version;

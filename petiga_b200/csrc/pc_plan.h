@@ -59,6 +59,7 @@ struct petiga_cuda_plan {
   double* d_rhs_own = nullptr;
   double* d_U_own = nullptr;
   double* d_V_own = nullptr;
+  double* d_scalar = nullptr; size_t scalar_cap = 0;   // [0,8): result, then per-CTA partials of compute_scalar
 
   struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
   int path = PETIGA_PATH_AUTO;

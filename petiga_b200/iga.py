@@ -282,6 +282,22 @@ class IGA:
     def ComputeIJacobian(self, a, V, t, U, J):
         _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(J.h)))
 
+    def ComputeScalar(self, U, n, scalar="CahnHilliard2D_Stats", ctx=()):
+        """IGAComputeScalar (src/petigacomp.c:35-96) with a device Scalar sentinel; ctx = the demo's AppCtx reals."""
+        fn = C.cast(getattr(self.H, "IGADeviceScalar_" + scalar), C.c_void_p)
+        S = (C.c_double * n)()
+        cx = (C.c_double * max(1, len(ctx)))(*ctx)
+        _chk(self.H.IGAComputeScalar(self.h, C.c_void_p(U.h if U is not None else None), n, S, fn, C.cast(cx, C.c_void_p)))
+        return np.array(list(S))
+
+    def ComputeErrorNorm(self, k, U=None, exact=None, ctx=()):
+        """IGAComputeErrorNorm (src/petigacomp.c:155-186); exact: None | "ErrNormTest" | "L2Projection"."""
+        fn = C.cast(getattr(self.H, "IGADeviceExact_" + exact), C.c_void_p) if exact else C.c_void_p(None)
+        out = (C.c_double * self.dof)()
+        cx = (C.c_double * max(1, len(ctx)))(*ctx)
+        _chk(self.H.IGAComputeErrorNorm(self.h, k, C.c_void_p(U.h if U is not None else None), fn, out, C.cast(cx, C.c_void_p)))
+        return np.array(list(out))
+
     # ---- introspection ----
     def info(self):
         buf = (C.c_int * 46)()
