@@ -44,6 +44,10 @@ typedef int PetscBool;
 #define PETSC_ERR_LIB 76
 #define PETSC_ERR_USER 83
 #define PETSC_ERR_ARG_NULL 85
+#define PETSC_ERR_FILE_OPEN 65
+#define PETSC_ERR_FILE_READ 66
+#define PETSC_ERR_FILE_WRITE 67
+#define PETSC_ERR_FILE_UNEXPECTED 79
 
 typedef struct { int rank, size; void *nccl; int device; } IGAComm;   /* stands in for MPI_Comm */
 
@@ -105,6 +109,14 @@ PetscErrorCode IGASetUp(IGA iga);
 /* geometry in natural ordering, i fastest, (n_d+1) control points per axis: X[..][nsd], W[..] or NULL.
    Stands in for IGALoadGeometry (src/petigaio.c:201-286), which reads the same arrays from a PETSc binary file. */
 PetscErrorCode IGASetGeometryArrays(IGA iga, PetscInt nsd, const PetscReal *X, const PetscReal *W);
+
+/* geometry / vector files in the reference's PETSc binary format (src/petigaio.c:11-139,201-369,535-735) */
+PetscErrorCode IGARead(IGA iga, const char filename[]);
+PetscErrorCode IGAWrite(IGA iga, const char filename[]);
+PetscErrorCode IGAReadVec(IGA iga, Vec vec, const char filename[]);
+PetscErrorCode IGAWriteVec(IGA iga, Vec vec, const char filename[]);
+/* the geometry the IGA holds, natural ordering: sizes[3] control points per axis, nsd, rational flag; X/W may be NULL */
+PetscErrorCode IGAGetGeometryArrays(IGA iga, PetscInt sizes[3], PetscInt *nsd, PetscBool *rational, PetscReal *X, PetscReal *W);
 
 /* ---- axis: include/petiga.h:62-89 ---- */
 PetscErrorCode IGAAxisSetPeriodic(IGAAxis axis, PetscBool periodic);

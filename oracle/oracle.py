@@ -241,6 +241,60 @@ class OracleIGA:
         return o
 
 
+def read_iga_file(filename):
+    """IGALoad + IGALoadGeometry (src/petigaio.c:11-73,201-286) restated with numpy: returns
+    (axes [(p, U)], nsd, X natural [..][nsd] or None, W natural or None, rational).  PETSc binary files are big-endian;
+    the geometry Vec holds (w*x, w) per control point in natural order and is de-homogenised on load (:259-266)."""
+    raw = open(filename, "rb").read()
+    pos = [0]
+
+    def ints(n):
+        v = np.frombuffer(raw, dtype=">i4", count=n, offset=pos[0]).astype(np.int64)
+        pos[0] += 4 * n
+        return v
+
+    def reals(n):
+        v = np.frombuffer(raw, dtype=">f8", count=n, offset=pos[0]).astype(np.float64)
+        pos[0] += 8 * n
+        return v
+
+    classid, info, dim = ints(3)
+    if classid != 1211299:                      # IGA_FILE_CLASSID (include/petiga.h:394)
+        raise ValueError("Not an IGA in file")  # :32
+    axes = []
+    for _ in range(dim):
+        p, m1 = ints(2)
+        axes.append((int(p), reals(int(m1))))
+    if not (info & 1):
+        return axes, 0, None, None, False
+    nsd = int(ints(1)[0])
+    vid, n = ints(2)
+    if vid != 1211214:                          # VEC_FILE_CLASSID
+        raise ValueError("Not a vector next in file")
+    sizes = [len(U) - 1 - p for p, U in axes]   # geom_sizes = m - p control points per axis
+    if n != int(np.prod(sizes)) * (nsd + 1):
+        raise ValueError("Vector in file different size than input vector")
+    Xw = reals(int(n)).reshape(-1, nsd + 1)
+    W = Xw[:, nsd].copy()
+    X = Xw[:, :nsd].copy()
+    nz = np.abs(W) > 0
+    X[nz] /= W[nz][:, None]                     # :262-264
+    rational = bool(W.max() - W.min() > 100 * np.finfo(float).eps)   # :251-253
+    shape = tuple(sizes[::-1])
+    return axes, nsd, X.reshape(shape + (nsd,)), W.reshape(shape), rational
+
+
+def oracle_from_file(filename, dof=1):
+    """An OracleIGA with the axes and geometry of an IGA file (what IGARead leaves behind)."""
+    axes, nsd, X, W, rational = read_iga_file(filename)
+    o = OracleIGA(len(axes), dof)
+    for d, (p, U) in enumerate(axes):
+        o.axis_knots(d, p, U)
+    if X is not None:
+        o.geometry(X, W)
+    return o
+
+
 def partition(size, rank, dim, N):
     L = lib()
     Na = (C.c_int * 3)(*(list(N) + [1, 1, 1])[:3])

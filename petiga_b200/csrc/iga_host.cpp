@@ -6,6 +6,7 @@
 //   processor grid + boxes         IGA_Partition / Stage1      (ref: src/petigapart.c, src/petiga.c:1111-1209)
 // Everything per-element runs on the GPU through libpetiga_cuda; there is no CPU assembly path here.
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -63,6 +64,7 @@ struct _p_IGA {
   int geom_sizes[3] = {1, 1, 1};
   // geometry (natural) and bc
   int nsd = 0; std::vector<double> geomX, geomW; bool rational = false;
+  std::vector<double> geomW_all;   // weights as given (kept even when constant, as iga->rationalW is; written back by IGAWrite)
   petiga_cuda_bc bc;
   Vec fixtable = nullptr;
   std::vector<double> fixtable_local;
@@ -542,6 +544,8 @@ PetscErrorCode IGASetGeometryArrays(IGA g, PetscInt nsd, const PetscReal* X, con
   g->geomX.assign(X, X + n * nsd);
   g->rational = false;
   g->geomW.clear();
+  g->geomW_all.clear();
+  if (W) g->geomW_all.assign(W, W + n);
   if (W) {
     double lo = W[0], hi = W[0];
     for (size_t k = 0; k < n; k++) { lo = std::min(lo, W[k]); hi = std::max(hi, W[k]); }
@@ -746,6 +750,184 @@ PetscErrorCode IGASetStream(IGA g, void* stream) {
   if (PetscErrorCode e = check(g)) return e;
   if (g->plan) return fail(PETSC_ERR_ORDER, "IGASetStream must be called before the first IGACreateMat/Vec/Compute");
   g->stream = stream;
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Geometry / vector files: the PETSc binary format the reference reads and writes (src/petigaio.c).  Everything is
+// big-endian (PetscBinaryRead/Write swap on little-endian hosts): PetscInt = int32, PetscReal/PetscScalar = float64.
+//   IGA file  (IGASave :75-139):  int IGA_FILE_CLASSID=1211299 | int info (bit0 geometry, bit1 property) | int dim |
+//                                 per axis { int p, int m+1, real U[m+1] } | [ int nsd | Vec ] | [ int npd | Vec ]
+//   Vec       (VecView binary):   int VEC_FILE_CLASSID=1211214 | int n | scalar[n]
+//   geometry Vec (:288-369):      natural order (i fastest) over the geom_sizes grid, per control point
+//                                 (w*x_0 .. w*x_{nsd-1}, w); IGALoadGeometry de-homogenises (:259-266)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kIGAFileClassId = 1211299, kVecFileClassId = 1211214;
+
+struct BinFile {
+  FILE* f = nullptr;
+  ~BinFile() { if (f) fclose(f); }
+  bool open(const char* name, const char* mode) { f = fopen(name, mode); return f != nullptr; }
+  static uint32_t swap32(uint32_t v) { return __builtin_bswap32(v); }
+  static uint64_t swap64(uint64_t v) { return __builtin_bswap64(v); }
+  bool read_int(int* v) { uint32_t u; if (fread(&u, 4, 1, f) != 1) return false; u = swap32(u); memcpy(v, &u, 4); return true; }
+  bool read_reals(double* v, size_t n) {
+    if (fread(v, 8, n, f) != n) return false;
+    for (size_t k = 0; k < n; k++) { uint64_t u; memcpy(&u, v + k, 8); u = swap64(u); memcpy(v + k, &u, 8); }
+    return true;
+  }
+  bool write_int(int v) { uint32_t u; memcpy(&u, &v, 4); u = swap32(u); return fwrite(&u, 4, 1, f) == 1; }
+  bool write_reals(const double* v, size_t n) {
+    for (size_t k = 0; k < n; k++) { uint64_t u; memcpy(&u, v + k, 8); u = swap64(u); if (fwrite(&u, 8, 1, f) != 1) return false; }
+    return true;
+  }
+};
+
+void reset_iga(IGA g) {   // IGAReset (src/petiga.c) as far as the mirror holds state
+  if (g->plan) { petiga_cuda_plan_destroy(g->plan); g->plan = nullptr; }
+  if (g->layout) { petiga_layout_destroy(g->layout); g->layout = nullptr; }
+  g->setup = 0;
+  g->nsd = 0; g->geomX.clear(); g->geomW.clear(); g->geomW_all.clear(); g->rational = false; g->geom_dirty = true;
+  g->fixtable = nullptr; g->fixtable_local.clear(); g->bc.fixtableU = nullptr; g->bc_dirty = true;
+}
+}  // namespace
+
+extern "C" {
+
+// IGARead -> IGALoad (src/petigaio.c:535-569, :11-73)
+PetscErrorCode IGARead(IGA g, const char filename[]) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!filename) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  BinFile bf;
+  if (!bf.open(filename, "rb")) return fail(PETSC_ERR_FILE_OPEN, std::string("Cannot open file ") + filename);
+  int classid = 0, info = 0, dim = 0;
+  if (!bf.read_int(&classid)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+  if (classid != kIGAFileClassId) return fail(PETSC_ERR_ARG_WRONG, "Not an IGA in file");          // :32
+  if (!bf.read_int(&info) || !bf.read_int(&dim)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+  const bool geometry = info & 0x1, property = info & 0x2;
+  reset_iga(g);
+  g->dim = -1;
+  if (PetscErrorCode e = IGASetDim(g, dim)) return e;
+  for (int i = 0; i < dim; i++) {
+    int p = 0, m1 = 0;
+    if (!bf.read_int(&p) || !bf.read_int(&m1) || m1 < 2 || m1 > (1 << 28)) return fail(PETSC_ERR_FILE_READ, "Bad axis record");
+    std::vector<double> U((size_t)m1);
+    if (!bf.read_reals(U.data(), U.size())) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+    IGAAxis ax = &g->axis[i];
+    ax->periodic = 0;                                       // IGAAxisInit: degree + knots; files carry no periodicity
+    ax->p = 0;
+    if (PetscErrorCode e = IGAAxisSetDegree(ax, p)) return e;
+    if (PetscErrorCode e = IGAAxisSetKnots(ax, m1 - 1, U.data())) return e;
+  }
+  for (int i = dim; i < 3; i++) { g->axis[i] = _n_IGAAxis(); g->axis[i].owner = g; }
+  if (geometry) {   // IGALoadGeometry :201-286
+    int nsd = 0;
+    if (!bf.read_int(&nsd)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+    if (nsd < 1 || nsd > 3) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Number of space dimensions must be in range [1,3]");
+    if (nsd < dim) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Number of space dimensions must greater than or equal to dim");
+    int vid = 0, n = 0;
+    if (!bf.read_int(&vid) || !bf.read_int(&n)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+    if (vid != kVecFileClassId) return fail(PETSC_ERR_ARG_WRONG, "Not a vector next in file");
+    size_t npts = 1;
+    for (int i = 0; i < dim; i++) npts *= (size_t)(g->axis[i].m - g->axis[i].p);
+    if ((size_t)n != npts * (nsd + 1)) return fail(PETSC_ERR_FILE_UNEXPECTED, "Vector in file different size than input vector");
+    std::vector<double> Xw((size_t)n), X(npts * nsd), W(npts);
+    if (!bf.read_reals(Xw.data(), Xw.size())) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+    for (size_t a = 0, pos = 0; a < npts; a++) {
+      for (int i = 0; i < nsd; i++) X[i + a * nsd] = Xw[pos++];
+      W[a] = Xw[pos++];
+      if (std::fabs(W[a]) > 0) for (int i = 0; i < nsd; i++) X[i + a * nsd] /= W[a];          // :262-264
+    }
+    if (PetscErrorCode e = IGASetGeometryArrays(g, nsd, X.data(), W.data())) return e;          // rational iff max(w)-min(w) > 100 eps (:251-253)
+  }
+  if (property) return fail(PETSC_ERR_SUP, "IGARead: property fields are not part of the device path");
+  return 0;
+}
+
+PetscErrorCode IGAGetGeometryArrays(IGA g, PetscInt sizes[3], PetscInt* nsd, PetscBool* rational, PetscReal* X, PetscReal* W) {
+  if (PetscErrorCode e = check(g)) return e;
+  for (int d = 0; d < 3; d++) if (sizes) sizes[d] = d < g->dim ? g->axis[d].m - g->axis[d].p : 1;
+  if (nsd) *nsd = g->nsd;
+  if (rational) *rational = g->rational ? PETSC_TRUE : PETSC_FALSE;
+  if (X && g->nsd) memcpy(X, g->geomX.data(), g->geomX.size() * sizeof(double));
+  if (W && g->nsd) { const size_t n = g->geomX.size() / g->nsd; for (size_t a = 0; a < n; a++) W[a] = g->geomW_all.empty() ? 1.0 : g->geomW_all[a]; }
+  return 0;
+}
+
+// IGAWrite -> IGASave (src/petigaio.c:571-597, :75-139); the file is written by rank 0 (every rank of the mirror holds the
+// full natural geometry arrays)
+PetscErrorCode IGAWrite(IGA g, const char filename[]) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!filename) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");          // IGACheckSetUpStage2
+  if (g->comm.rank != 0) return 0;
+  BinFile bf;
+  if (!bf.open(filename, "wb")) return fail(PETSC_ERR_FILE_OPEN, std::string("Cannot open file ") + filename);
+  bool ok = bf.write_int(kIGAFileClassId) && bf.write_int(g->nsd ? 0x1 : 0x0) && bf.write_int(g->dim);
+  for (int i = 0; ok && i < g->dim; i++) {
+    const _n_IGAAxis& ax = g->axis[i];
+    ok = bf.write_int(ax.p) && bf.write_int(ax.m + 1) && bf.write_reals(ax.U.data(), (size_t)ax.m + 1);
+  }
+  if (ok && g->nsd) {   // IGASaveGeometry :288-369
+    const int nsd = g->nsd;
+    const size_t npts = g->geomX.size() / nsd;
+    std::vector<double> Xw(npts * (nsd + 1));
+    for (size_t a = 0, pos = 0; a < npts; a++) {
+      const bool hasW = !g->geomW_all.empty();
+      const double w = (hasW && std::fabs(g->geomW_all[a]) > 0) ? g->geomW_all[a] : 1.0;
+      for (int i = 0; i < nsd; i++) Xw[pos++] = g->geomX[i + a * nsd] * w;
+      Xw[pos++] = hasW ? g->geomW_all[a] : 1.0;
+    }
+    ok = bf.write_int(nsd) && bf.write_int(kVecFileClassId) && bf.write_int((int)Xw.size()) && bf.write_reals(Xw.data(), Xw.size());
+  }
+  if (!ok) return fail(PETSC_ERR_FILE_WRITE, "Error writing to file");
+  return 0;
+}
+
+// natural index (i fastest over the global node grid) of this rank's owned nodes, in owned order
+static void owned_natural(IGA g, std::vector<size_t>& nat) {
+  const int* ls = g->node_lstart; const int* lw = g->node_lwidth;
+  const size_t n0 = g->axis[0].nnp, n1 = g->axis[1].nnp;
+  nat.clear();
+  for (int k = 0; k < lw[2]; k++) for (int j = 0; j < lw[1]; j++) for (int i = 0; i < lw[0]; i++)
+    nat.push_back((size_t)(ls[0] + i) + n0 * ((size_t)(ls[1] + j) + n1 * (size_t)(ls[2] + k)));
+}
+
+// IGAReadVec -> IGALoadVec (src/petigaio.c:685-709, :644-662): file holds the natural vector; every rank reads its part
+PetscErrorCode IGAReadVec(IGA g, Vec vec, const char filename[]) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!vec || !filename) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  BinFile bf;
+  if (!bf.open(filename, "rb")) return fail(PETSC_ERR_FILE_OPEN, std::string("Cannot open file ") + filename);
+  int vid = 0, n = 0;
+  if (!bf.read_int(&vid) || !bf.read_int(&n)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+  if (vid != kVecFileClassId) return fail(PETSC_ERR_ARG_WRONG, "Not a vector next in file");
+  const size_t ntot = (size_t)g->axis[0].nnp * g->axis[1].nnp * g->axis[2].nnp * g->dof;
+  if ((size_t)n != ntot) return fail(PETSC_ERR_FILE_UNEXPECTED, "Vector in file different size than input vector");
+  std::vector<double> nat_v(ntot), own((size_t)vec->n);
+  if (!bf.read_reals(nat_v.data(), ntot)) return fail(PETSC_ERR_FILE_READ, "Read past end of file");
+  std::vector<size_t> nat;
+  owned_natural(g, nat);
+  for (size_t a = 0; a < nat.size(); a++) for (int c = 0; c < g->dof; c++) own[a * g->dof + c] = nat_v[nat[a] * g->dof + c];
+  return VecSetArrayHost(vec, own.data());
+}
+
+// IGAWriteVec -> IGASaveVec (src/petigaio.c:711-735, :664-683)
+PetscErrorCode IGAWriteVec(IGA g, Vec vec, const char filename[]) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!vec || !filename) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  if (g->comm.size > 1) return fail(PETSC_ERR_SUP, "IGAWriteVec: gathering a distributed vector to the natural ordering is not available in the mirror");
+  std::vector<double> own((size_t)vec->n);
+  if (PetscErrorCode e = VecGetArrayHost(vec, own.data())) return e;
+  BinFile bf;
+  if (!bf.open(filename, "wb")) return fail(PETSC_ERR_FILE_OPEN, std::string("Cannot open file ") + filename);
+  if (!(bf.write_int(kVecFileClassId) && bf.write_int(vec->n) && bf.write_reals(own.data(), own.size())))
+    return fail(PETSC_ERR_FILE_WRITE, "Error writing to file");
   return 0;
 }
 

@@ -282,6 +282,32 @@ class IGA:
     def ComputeIJacobian(self, a, V, t, U, J):
         _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(J.h)))
 
+    # ---- files (src/petigaio.c) ----
+    def Read(self, filename):
+        _chk(self.H.IGARead(self.h, filename.encode()))
+        d = C.c_int()
+        _chk(self.H.IGAGetDim(self.h, C.byref(d)))
+        self.dim = d.value
+
+    def Write(self, filename):
+        _chk(self.H.IGAWrite(self.h, filename.encode()))
+
+    def ReadVec(self, vec, filename):
+        _chk(self.H.IGAReadVec(self.h, C.c_void_p(vec.h), filename.encode()))
+
+    def WriteVec(self, vec, filename):
+        _chk(self.H.IGAWriteVec(self.h, C.c_void_p(vec.h), filename.encode()))
+
+    def GetGeometryArrays(self):
+        sizes, nsd, rat = (C.c_int * 3)(), C.c_int(), C.c_int()
+        _chk(self.H.IGAGetGeometryArrays(self.h, sizes, C.byref(nsd), C.byref(rat), None, None))
+        n = sizes[0] * sizes[1] * sizes[2]
+        if nsd.value == 0:
+            return list(sizes), 0, False, None, None
+        X, W = np.zeros(n * nsd.value), np.zeros(n)
+        _chk(self.H.IGAGetGeometryArrays(self.h, sizes, C.byref(nsd), C.byref(rat), X.ctypes.data_as(_dp), W.ctypes.data_as(_dp)))
+        return list(sizes), nsd.value, bool(rat.value), X.reshape(n, nsd.value), W
+
     def ComputeScalar(self, U, n, scalar="CahnHilliard2D_Stats", ctx=()):
         """IGAComputeScalar (src/petigacomp.c:35-96) with a device Scalar sentinel; ctx = the demo's AppCtx reals."""
         fn = C.cast(getattr(self.H, "IGADeviceScalar_" + scalar), C.c_void_p)
