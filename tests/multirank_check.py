@@ -37,6 +37,7 @@ def main():
     cases = [
         ("poisson3d p2", Case(3, p=2, N=8, bcv=dall(3)), "SYSTEM", "POISSON", [], False),
         ("poisson3d p3", Case(3, p=3, N=(9, 8, 10), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("poisson3d p3 big", Case(3, p=3, N=(24, 20, 22), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
         ("poisson2d p2", Case(2, p=2, N=(16, 12), bcv=dall(2, 0.5)), "SYSTEM", "POISSON", [], False),
         ("elasticity3d", Case(3, dof=3, p=2, N=6, bcv=[(0, 0, 0, 0.0), (0, 0, 1, 0.0), (0, 0, 2, 0.0), (0, 1, 0, 1.0)]), "SYSTEM", "ELASTICITY3D", [1.0, 1.0], False),
         ("elasticity3d aij", Case(3, dof=3, p=2, N=6, mattype="aij", bcv=[(0, 0, 0, 0.0), (0, 1, 0, 1.0)]), "SYSTEM", "ELASTICITY3D", [1.0, 1.0], False),
@@ -83,6 +84,43 @@ def main():
                 print("%-20s %-10s path=%d %s%s" % (name, path, res["path"], "ok " if flag.item() == 0 else "FAIL", msg), flush=True)
             nfail += int(flag.item() != 0)
             g.Destroy()
+    # ---- IGAComputeScalar / IGAComputeErrorNorm: state halo + ncclAllReduce (src/petigacomp.c:35-186) ----
+    scalars = [
+        ("errnorm 3d k=1", Case(3, dof=4, p=2, N=6, order=2), "ERRNORM", [1, 1, 0], 4),
+        ("errnorm mapped k=2", Case(2, dof=4, p=3, N=8, order=2, geometry=("perturbed", 0.05)), "ERRNORM", [2, 1, 0], 4),
+        ("ch stats", Case(2, p=2, N=32, C=1, periodic=True, order=2), "CH_STATS", [1.5, 3000.0, 0.63], 3),
+    ]
+    for name, case, sid, prm, n in scalars:
+        o = case.oracle()
+        o.setup()
+        rp, ci, rs = o.pattern(world)
+        nn = len(rp) - 1
+        if sid == "CH_STATS":
+            U, _ = state_vectors(nn)
+        else:
+            U = np.random.default_rng(9).standard_normal((nn, case.dof))
+        exp = o.compute_scalar(sid, prm, n, U=U, size=world)
+        r0, r1 = int(rs[rank]), int(rs[rank + 1])
+        g = case.product(rank=rank, size=world, nccl=comm.value, device=local)
+        vU = g.CreateVec()
+        vU.set(np.asarray(U).reshape(nn, -1)[r0:r1].reshape(-1))
+        if sid == "CH_STATS":
+            got = g.ComputeScalar(vU, 3, "CahnHilliard2D_Stats", prm)
+            err = max(abs(got[0] - exp[0]) / abs(exp[0]), abs(got[1] - exp[1]) / abs(exp[1]), abs(got[2] - exp[2]) / abs(exp[1]))
+        else:
+            got = g.ComputeErrorNorm(int(prm[0]), vU, "ErrNormTest") ** 2
+            err = float(np.max(np.abs(got - exp) / np.abs(exp)))
+        ok = err <= 1e-11
+        allg = [None] * world
+        dist.all_gather_object(allg, [float(x) for x in got])
+        ok &= all(a == allg[0] for a in allg)            # every rank holds the same sums (MPI_Allreduce semantics)
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print("%-20s scalar     %s err=%.1e" % (name, "ok " if flag.item() == 0 else "FAIL", err), flush=True)
+        nfail += int(flag.item() != 0)
+        vU.destroy()
+        g.Destroy()
     dist.barrier()
     if rank == 0:
         print("MULTIRANK %s: %d failures on %d ranks" % ("PASS" if nfail == 0 else "FAIL", nfail, world), flush=True)
