@@ -169,8 +169,11 @@ PetscErrorCode IGAComputeErrorNorm(IGA iga, PetscInt k, Vec vecU, IGAFormExact E
 PetscErrorCode IGAGetInfoArray(IGA iga, PetscInt info[46]);     /* same layout as the oracle's oiga_get_info */
 PetscErrorCode IGAGetBasisTable(IGA iga, PetscInt axis, PetscInt which, PetscReal *out);  /* 0 value,1 weight,2 point,3 detJac,4 knots */
 PetscErrorCode IGAGetLGMapHost(IGA iga, PetscInt *lgmap);
-PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* forwarded to petiga_cuda_set_option */
+PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* forwarded to petiga_cuda_set_option; "async" = 1:
+                                                                                 IGACompute* only enqueue on the IGA's stream (device-
+                                                                                 resident hand-off to a GPU solve) */
 PetscErrorCode IGAGetStat(IGA iga, const char *name, PetscReal *value);
+PetscErrorCode IGASynchronize(IGA iga);                                        /* wait for the IGA's stream (after IGASetOption(iga,"async",1)) */
 PetscErrorCode IGASetStream(IGA iga, void *cuda_stream);                      /* stream all device work is enqueued on */
 void *IGAGetLayout(IGA iga);                                                 /* the petiga_layout behind the IGA */
 PetscErrorCode IGAGetPlan(IGA iga, void **plan);                             /* the petiga_cuda_plan behind the IGA */

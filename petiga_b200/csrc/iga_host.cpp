@@ -74,6 +74,7 @@ struct _p_IGA {
   petiga_cuda_plan* plan = nullptr;
   void* stream = nullptr;
   std::vector<std::pair<std::string, double>> options;
+  bool async = false;   // IGASetOption("async",1): the drivers only enqueue; IGASynchronize / host getters wait
 };
 
 namespace {
@@ -632,7 +633,8 @@ PetscErrorCode MatGetSizesIGA(Mat A, PetscInt* nrows, int64_t* nnz, PetscInt* bs
 }
 PetscErrorCode MatGetCSRHost(Mat A, PetscInt* rowptr, PetscInt* colidx, PetscScalar* values) {
   if (!A) return fail(PETSC_ERR_ARG_NULL, "Null Mat");
-  int rc = 0;
+  int rc = A->iga->plan ? petiga_cuda_finish(A->iga->plan) : 0;
+  if (rc) return from_cuda(rc);
   if (rowptr) rc = petiga_cuda_memcpy_d2h(rowptr, A->d_rowptr, ((size_t)A->nrows + 1) * sizeof(int));
   if (!rc && colidx) rc = petiga_cuda_memcpy_d2h(colidx, A->d_colidx, (size_t)A->nnz * sizeof(int));
   if (!rc && values) {
@@ -643,7 +645,7 @@ PetscErrorCode MatGetCSRHost(Mat A, PetscInt* rowptr, PetscInt* colidx, PetscSca
 }
 PetscErrorCode MatGetValuesDevice(Mat A, PetscScalar** d) { if (!A || !d) return fail(PETSC_ERR_ARG_NULL, "Null"); *d = A->d_values; return 0; }
 PetscErrorCode VecGetLocalSize(Vec v, PetscInt* n) { if (!v || !n) return fail(PETSC_ERR_ARG_NULL, "Null"); *n = v->n; return 0; }
-PetscErrorCode VecGetArrayHost(Vec v, PetscScalar* out) { if (!v || !out) return fail(PETSC_ERR_ARG_NULL, "Null"); return from_cuda(petiga_cuda_memcpy_d2h(out, v->d, (size_t)v->n * sizeof(double))); }
+PetscErrorCode VecGetArrayHost(Vec v, PetscScalar* out) { if (!v || !out) return fail(PETSC_ERR_ARG_NULL, "Null"); if (v->iga->plan) petiga_cuda_finish(v->iga->plan); return from_cuda(petiga_cuda_memcpy_d2h(out, v->d, (size_t)v->n * sizeof(double))); }
 PetscErrorCode VecSetArrayHost(Vec v, const PetscScalar* in) { if (!v || !in) return fail(PETSC_ERR_ARG_NULL, "Null"); return from_cuda(petiga_cuda_memcpy_h2d(v->d, in, (size_t)v->n * sizeof(double))); }
 PetscErrorCode VecGetArrayDevice(Vec v, PetscScalar** d) { if (!v || !d) return fail(PETSC_ERR_ARG_NULL, "Null"); *d = v->d; return 0; }
 
@@ -654,7 +656,12 @@ static PetscErrorCode run(IGA g, int slot, PetscReal a, Vec V, PetscReal t, Vec 
   if (PetscErrorCode e = ensure_plan(g)) return e;
   int rc = petiga_cuda_compute(g->plan, slot, A ? A->baij : 0, a, V ? V->d : nullptr, t, U ? U->d : nullptr, A ? A->d_values : nullptr, B ? B->d : nullptr);
   if (rc) return from_cuda(rc);
+  if (g->async) return 0;                          // device-resident hand-off: ordered on the IGA's stream, no host wait
   return from_cuda(petiga_cuda_finish(g->plan));   // Mat/VecAssemblyEnd: fully assembled on return
+}
+PetscErrorCode IGASynchronize(IGA g) {
+  if (PetscErrorCode e = check(g)) return e;
+  return g->plan ? from_cuda(petiga_cuda_finish(g->plan)) : 0;
 }
 PetscErrorCode IGAComputeVector(IGA g, Vec B) { if (!B) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_VECTOR, 0, nullptr, 0, nullptr, nullptr, B); }
 PetscErrorCode IGAComputeMatrix(IGA g, Mat A) { if (!A) return fail(PETSC_ERR_ARG_NULL, "Null Mat"); return run(g, PETIGA_SLOT_MATRIX, 0, nullptr, 0, nullptr, A, nullptr); }
@@ -728,6 +735,7 @@ PetscErrorCode IGAGetLGMapHost(IGA g, PetscInt* lgmap) {
 }
 PetscErrorCode IGASetOption(IGA g, const char* name, PetscReal value) {
   if (PetscErrorCode e = check(g)) return e;
+  if (!strcmp(name, "async")) { g->async = value != 0; return 0; }
   for (auto& o : g->options) if (o.first == name) { o.second = value; goto done; }
   g->options.emplace_back(name, value);
 done:

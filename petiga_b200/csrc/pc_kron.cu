@@ -37,6 +37,7 @@ struct KronParams {
   const double* mv[3];    // [2][nnp]         1-D load vectors  sum_e sum_q wJ N^{(r)}
   const int* nsup[3];     // [nnp]            elements containing basis i
   const double* lsum[3];  // [nnp]            sum over those elements of detJac/nen
+  const double* rsum[3];  // [4][nnp]         row sums of M (all columns of the row)
   const int* first[3];    // [nnp]
   const int* Wg[3];       // [gw] widths by ghost coordinate
   const int* lo[3];       // [gw]
@@ -112,6 +113,14 @@ __global__ void kron_1d_kernel(DevAxis ax, const int* __restrict__ first, double
   }
 }
 
+__global__ void kron_rowsum_kernel(const double* __restrict__ M, double* __restrict__ rsum, int nnp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // t = rs*nnp + i
+  if (t >= 4 * nnp) return;
+  double acc = 0.0;
+  for (int c = 0; c < kMaxW; c++) acc += M[(size_t)t * kMaxW + c];
+  rsum[t] = acc;
+}
+
 // Dirichlet data of a node from its per-axis boundary codes (0 interior, 1 side 0, 2 side 1): the last face in the
 // reference's order (axis ascending, side 0 then 1) wins (AddFixa overwrites, petigaelem.c:1166-1189).
 template <int DOF>
@@ -140,9 +149,12 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
-  __shared__ double jkval[kMaxWW];               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
+  __shared__ double jkval[kMaxWW];
+  __shared__ double Gm[2][kMaxWW];               // DOF == 1: G0/G3 with the Dirichlet (j,k) columns zeroed; Hs = sum over those columns of G*value
+  __shared__ double Hs[2];               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
   __shared__ double stage[(DOF > 1) ? 8 * 32 * DOF * DOF : 1];
-  const int Aj = kp.ls[1] + (int)(blockIdx.x % kp.lw[1]), Ak = kp.ls[2] + (int)(blockIdx.x / kp.lw[1]);
+  const int pencil = (int)blockIdx.x;
+  const int Aj = kp.ls[1] + pencil % kp.lw[1], Ak = kp.ls[2] + pencil / kp.lw[1];
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
   const int Wj = kp.Wg[1][gj], Wk = kp.Wg[2][gk], Wjk = Wj * Wk;
   const int fj = kp.first[1][Aj], fk = kp.first[2][Ak];
@@ -203,15 +215,37 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
   // full-width rows (W_i = 2p+1, all but the first/last p rows of a pencil): lane -> (column offset, group) fixed per warp
   const int WiF = kp.wfull0, ngrpF = 32 / WiF, grpF = lane / WiF, ciF = lane - grpF * WiF;
   const int ostepF = ngrpF * WiF, offF = grpF * WiF + ciF, nfullF = Wjk / ngrpF;   // every group runs nfullF full iterations
-  // ---- interior stretch of an interior pencil: 4 rows per warp pass share the G loads; no per-row tests ----
+  // ---- interior stretch of a pencil whose own node is not on a Dirichlet face: 4 rows per warp pass share the G loads;
+  //      no per-row tests.  Columns on Dirichlet (j,k) faces are handled by the masked tables Gm (stored value 0) and their
+  //      contribution to the right-hand side is separable:  -rowsum(M0^{00})*H0 - rowsum(M0^{11})*H3 ----
   int nfast = 0;
   const int fast_lo = kp.fast_lo;
   if (PF > 0) {
     constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC, RW = WIC * WJKC, R = 4;
-    const bool pencil_fast = fast_ok && simple_jk && !jk_boundary && !(fixing && (rcj || rck)) && Wjk == WJKC && WiF == WIC && kp.fast_hi > fast_lo;
+    const bool pencil_fast = fast_ok && simple_jk && !(fixing && (rcj || rck)) && Wjk == WJKC && WiF == WIC && kp.fast_hi > fast_lo &&
+                             !(jk_boundary && (kp.fixtable || !want_vec));
     if (pencil_fast) {
+      if (jk_boundary) {   // uniform over the CTA
+        if (warp == 0) {
+          double h0 = 0.0, h3 = 0.0;
+          for (int t = lane; t < Wjk; t += 32) {
+            const bool fx = jkinfo[t] & 32;
+            const double g0 = G[0][0][t], g3 = G[3][0][t];
+            if (fx) { h0 = fma(g0, jkval[t], h0); h3 = fma(g3, jkval[t], h3); }
+            Gm[0][t] = fx ? 0.0 : g0;
+            Gm[1][t] = fx ? 0.0 : g3;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { h0 += __shfl_xor_sync(0xffffffffu, h0, o); h3 += __shfl_xor_sync(0xffffffffu, h3, o); }
+          if (lane == 0) { Hs[0] = h0; Hs[1] = h3; }
+        }
+        __syncthreads();
+      }
       nfast = kp.fast_hi - fast_lo;
       const int64_t base_lo = __ldg(rowbase + lr0 + fast_lo);
+      const double* __restrict__ g0 = jk_boundary ? &Gm[0][grpF] : &G[0][0][grpF];
+      const double* __restrict__ g3 = jk_boundary ? &Gm[1][grpF] : &G[3][0][grpF];
+      const double H0 = jk_boundary ? Hs[0] : 0.0, H3 = jk_boundary ? Hs[1] : 0.0;
       for (int il = fast_lo + warp * R; il < kp.fast_hi; il += nwarps * R) {
         if (grpF < NGRP) {
           double a0[R], a3[R];
@@ -221,8 +255,6 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
             a3[r] = __ldg(M0 + ((size_t)3 * nnp0 + ls0 + il + r) * kMaxW + ciF);
           }
           double* __restrict__ rowp = values + base_lo + (int64_t)(il - fast_lo) * RW + offF;
-          const double* __restrict__ g0 = &G[0][0][grpF];
-          const double* __restrict__ g3 = &G[3][0][grpF];
 #pragma unroll
           for (int k = 0; k < NITER; k++)
             if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) {
@@ -242,6 +274,7 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
               F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
             }
           }
+          if (jk_boundary) F -= __ldg(kp.rsum[0] + Ai) * H0 + __ldg(kp.rsum[0] + (size_t)3 * nnp0 + Ai) * H3;
           rhs[lr0 + il + lane] = F;
         }
       }
@@ -657,14 +690,16 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
       const int nnp = L.ax[d].nnp;
       void* buf = nullptr;
       const size_t nM = (size_t)4 * nnp * kMaxW, nmv = (size_t)2 * nnp;
-      PC_CUDA(cudaMalloc(&buf, (nM + nmv + nnp) * sizeof(double) + (size_t)nnp * sizeof(int)));
+      PC_CUDA(cudaMalloc(&buf, (nM + nmv + nnp + (size_t)4 * nnp) * sizeof(double) + (size_t)nnp * sizeof(int)));
       P->allocs.push_back(buf);
       P->d_kronrow[d] = (double*)buf;
-      double* M = (double*)buf; double* mv = M + nM; double* lsum = mv + nmv; int* nsup = (int*)(lsum + nnp);
+      double* M = (double*)buf; double* mv = M + nM; double* lsum = mv + nmv; double* rsum = lsum + nnp; int* nsup = (int*)(rsum + (size_t)4 * nnp);
       const int total = (int)nM;
       kron_1d_kernel<<<(total + 127) / 128, 128, 0, P->stream>>>(P->dax[d], P->d_first[d], M, mv, nsup, lsum);
       PC_CUDA(cudaGetLastError());
-      P->launches++;
+      kron_rowsum_kernel<<<(4 * nnp + 127) / 128, 128, 0, P->stream>>>(M, rsum, nnp);
+      PC_CUDA(cudaGetLastError());
+      P->launches += 2;
     }
   }
   // the parameter block only depends on (slot, form, parameters, block layout, boundary conditions): build it once and
@@ -682,7 +717,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
   for (int d = 0; d < 3; d++) {
     const int nnp = L.ax[d].nnp;
     const size_t nM = (size_t)4 * nnp * kMaxW, nmv = (size_t)2 * nnp;
-    kp.M[d] = P->d_kronrow[d]; kp.mv[d] = kp.M[d] + nM; kp.lsum[d] = kp.mv[d] + nmv; kp.nsup[d] = (const int*)(kp.lsum[d] + nnp);
+    kp.M[d] = P->d_kronrow[d]; kp.mv[d] = kp.M[d] + nM; kp.lsum[d] = kp.mv[d] + nmv; kp.rsum[d] = kp.lsum[d] + nnp; kp.nsup[d] = (const int*)(kp.rsum[d] + (size_t)4 * nnp);
     kp.first[d] = P->d_first[d]; kp.Wg[d] = P->dax[d].W; kp.lo[d] = P->dax[d].lo; kp.seg[d] = P->dax[d].seg; kp.simp[d] = P->dax[d].simple;
     kp.ls[d] = L.ax[d].ls; kp.lw[d] = L.ax[d].lw; kp.gs[d] = L.ax[d].gs; kp.gw[d] = L.ax[d].gw; kp.nnp[d] = nnp; kp.periodic[d] = L.ax[d].periodic;
     if (L.ax[d].periodic) simple = false;

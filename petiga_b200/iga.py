@@ -282,6 +282,9 @@ class IGA:
     def ComputeIJacobian(self, a, V, t, U, J):
         _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(J.h)))
 
+    def Synchronize(self):
+        _chk(self.H.IGASynchronize(self.h))
+
     # ---- files (src/petigaio.c) ----
     def Read(self, filename):
         _chk(self.H.IGARead(self.h, filename.encode()))

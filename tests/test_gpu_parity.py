@@ -186,6 +186,27 @@ def test_nurbs_quarter_annulus(form, params):
         assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6
 
 
+# ---- separable path, multi-row interior passes with masked Dirichlet columns (needs >= 2p+1+4 nodes per axis) ---------
+def test_poisson3d_p3_separable_interior_passes_vs_oracle():
+    """Different Dirichlet values per face (precedence k over j over i) and one free face; mesh large enough for the
+    4-row passes of kron_rows_kernel, small enough for the oracle."""
+    bcv = [(0, 0, 0, 0.25), (0, 1, 0, -1.5), (1, 0, 0, 2.0), (2, 0, 0, 0.5), (2, 1, 0, 3.0)]
+    case = Case(3, p=3, N=(14, 12, 13), bcv=bcv, bcl=[(1, 1, 0, 0.75)])
+    res, _ = check_against_oracle(case, "SYSTEM", "POISSON", path="auto", tol=TOL)
+    assert res["path"] == 2
+
+
+@pytest.mark.parametrize("p,N", [(3, 24), (2, 20), (4, 18)])
+def test_poisson3d_separable_equals_quadrature_midsize(p, N):
+    bcv = [(d, s, 0, 1.0 + d - 0.5 * s) for d in range(3) for s in range(2)]
+    case = Case(3, p=p, N=N, bcv=bcv)
+    a = run_product(case, "SYSTEM", "POISSON", path="auto")
+    b = run_product(case, "SYSTEM", "POISSON", path="quadrature")
+    assert a["path"] == 2 and b["path"] == 1
+    from tests.common import rel_frobenius
+    assert rel_frobenius(a["values"], b["values"]) <= TOL and rel_frobenius(a["rhs"], b["rhs"]) <= TOL
+
+
 # ---- size-independent properties at BASELINE's full cfg-2 size (the oracle cannot run 128^3 in seconds) -------
 def test_cfg2_full_size_properties():
     import petiga_b200 as pb
