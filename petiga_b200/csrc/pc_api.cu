@@ -445,7 +445,6 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
           fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
         }
         if (fs.vcount || fs.lcount) kp.any_bc = 1;
-        if (fs.lcount && P->d_X) { set_error("compute: boundary loads on a mapped geometry (BoundaryArea) are not available on the device path yet"); return PETIGA_CUDA_ERR_SUP; }
       }
   kp.form = form; kp.slot = slot; kp.block = block;
   kp.mc0 = fi.mc0; kp.mc1 = quad_mat ? fi.mc1 : fi.mc0; kp.vc0 = fi.vc0; kp.vc1 = fi.vc1;

@@ -141,7 +141,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
               if (DIM > 1) {
                 for (int e = 0; e < DIM; e++)
                   if (e != d) A *= prm.ax[e].detJac[ID[e]] / (double)NEN1;
-                A *= (DIM == 2) ? 2 : 4;
+                A *= mapped ? face_area_factor<DIM>(prm.ax, ID, d, s, prm.X, prm.Wt) : ((DIM == 2) ? 2.0 : 4.0);
               }
               for (int k = 0; k < fs.lcount; k++) vflux[fs.lfield[k]] += fs.lvalue[k] * A;
             }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
               double A = 1.0;
               if (DIM > 1) {
                 for (int e = 0; e < DIM; e++) if (e != d) A *= prm.ax[e].detJac[ID[e]] / (double)NEN1;
-                A *= (DIM == 2) ? 2 : 4;
+                A *= mapped ? face_area_factor<DIM>(prm.ax, ID, d, s, prm.X, prm.Wt) : ((DIM == 2) ? 2.0 : 4.0);
               }
               for (int k = 0; k < fs.lcount; k++)
 #pragma unroll

@@ -186,6 +186,36 @@ def test_nurbs_quarter_annulus(form, params):
         assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6
 
 
+# ---- Neumann loads on a mapped geometry: BoundaryArea integrates the surface Jacobian (petigaelem.c:1132-1162) ------
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_boundary_loads_on_mapped_geometry(dim, impl):
+    bcv = [(0, 0, c, 0.0) for c in range(dim)]
+    bcl = [(0, 1, 0, 1.0), (1, 0, dim - 1, -0.5), (dim - 1, 1, 0, 0.25)]
+    case = Case(dim, dof=dim, p=2, N=5, order=1, geometry=("perturbed", 0.05), bcv=bcv, bcl=bcl)
+    check_against_oracle(case, "SYSTEM", "ELASTICITY", [1.0, 1.0], path="quadrature", tol=TOL, quad_impl=impl)
+
+
+def test_boundary_loads_on_nurbs_annulus():
+    import petiga_b200 as pb
+    from oracle.oracle import OracleIGA
+    from tests.geomutil import refine_annulus
+    from tests.common import rel_frobenius
+    o, X, W = refine_annulus(OracleIGA, N=(5, 4))
+    g, _, _ = refine_annulus(pb.IGA, N=(5, 4))
+    for obj, bv, bl in ((o, o.boundary_value, o.boundary_load), (g, g.SetBoundaryValue, g.SetBoundaryLoad)):
+        bv(0, 0, 0, 1.0)
+        bl(0, 1, 0, 2.0)      # outer arc r = 2: total load = 2 * (pi/2 * 2)
+        bl(1, 0, 0, -1.0)
+    o.setup()
+    Ko, Fo = o.assemble("SYSTEM", "POISSON")
+    g.SetUp()
+    g.SetForm("SYSTEM", "POISSON")
+    A, B = g.CreateMat(), g.CreateVec()
+    g.ComputeSystem(A, B)
+    assert rel_frobenius(A.values(), Ko.reshape(-1)) <= TOL and rel_frobenius(B.get(), Fo.reshape(-1)) <= TOL
+
+
 # ---- separable path, multi-row interior passes with masked Dirichlet columns (needs >= 2p+1+4 nodes per axis) ---------
 def test_poisson3d_p3_separable_interior_passes_vs_oracle():
     """Different Dirichlet values per face (precedence k over j over i) and one free face; mesh large enough for the
