@@ -140,6 +140,9 @@ int petiga_cuda_get_stat(petiga_cuda_plan *plan, const char *name, double *value
    nsd must equal dim.  Pass X == NULL to return to the identity map. */
 int petiga_cuda_set_geometry(petiga_cuda_plan *plan, int nsd, const double *X, const double *W);
 int petiga_cuda_set_bc(petiga_cuda_plan *plan, const petiga_cuda_bc *bc);
+/* IGASetFixTable with the table as a *global device vector* (this rank's owned part [owned nodes * dof]): the library does
+   the global-to-local scatter itself (NCCL halo on more than one rank).  Call after petiga_cuda_set_bc; NULL clears it. */
+int petiga_cuda_set_fixtable_device(petiga_cuda_plan *plan, const double *table_own);
 int petiga_cuda_form_select(petiga_cuda_plan *plan, int slot, int form_id, const double *params, int nparams);
 
 /* ---- pattern (IGACreateMat) ----

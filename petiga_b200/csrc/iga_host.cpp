@@ -227,21 +227,12 @@ PetscErrorCode ensure_plan(IGA g) {
   if (g->bc_dirty) {
     petiga_cuda_bc bc = g->bc;
     bc.fixtableU = nullptr;
-    if (g->fixtable) {   // G2L of the table (IGASetFixTable -> IGAGlobalToLocal); single-rank gather through the lgmap
-      if (g->comm.size > 1) return fail(PETSC_ERR_SUP, "IGASetFixTable on more than one rank is not wired in the host mirror");
-      int nown, ng; int64_t nnz;
-      petiga_cuda_plan_sizes(g->plan, &nown, &ng, &nnz);
-      std::vector<int> lg(ng);
-      petiga_cuda_plan_lgmap_host(g->plan, lg.data());
-      std::vector<double> glob((size_t)nown * g->dof);
-      int rc = petiga_cuda_memcpy_d2h(glob.data(), g->fixtable->d, glob.size() * sizeof(double));
-      if (rc) return from_cuda(rc);
-      g->fixtable_local.resize((size_t)ng * g->dof);
-      for (int a = 0; a < ng; a++) for (int c = 0; c < g->dof; c++) g->fixtable_local[(size_t)a * g->dof + c] = glob[(size_t)lg[a] * g->dof + c];
-      bc.fixtableU = g->fixtable_local.data();
-    }
     int rc = petiga_cuda_set_bc(g->plan, &bc);
     if (rc) return from_cuda(rc);
+    if (g->fixtable) {   // IGASetFixTable -> IGAGlobalToLocal: the library scatters the device vector (NCCL halo when distributed)
+      rc = petiga_cuda_set_fixtable_device(g->plan, g->fixtable->d);
+      if (rc) return from_cuda(rc);
+    }
     g->bc_dirty = false;
   }
   for (int s = 0; s < PETIGA_NSLOTS; s++)

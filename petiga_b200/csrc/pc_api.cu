@@ -74,6 +74,14 @@ __global__ void gather_owned_kernel(const double* __restrict__ src, double* __re
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// IGASetFixTable: local-row vector -> ghost-box table [ghost box][dof] (the G2L scatter of src/petigaform.c IGASetFixTable)
+__global__ void fixtable_scatter_kernel(const int* __restrict__ localrow, const double* __restrict__ loc, double* __restrict__ out, size_t ng, int dof) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ng * dof; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = i / dof;
+    out[i] = loc[(size_t)localrow[g] * dof + (i - g * dof)];
+  }
+}
+
 // FP64 FMA peak: 8 independent DFMA chains per thread, 4 CTAs of 256 threads per SM (the roofline denominator of the
 // quadrature kernels; MEASURED_PEAKS.json carries no FP64 figure, SURVEY 8d asks for a measured one)
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
@@ -273,6 +281,34 @@ int petiga_cuda_set_bc(petiga_cuda_plan* P, const petiga_cuda_bc* bc) {
     PC_CUDA(cudaMalloc(&P->d_fixtable, n * sizeof(double)));
     PC_CUDA(cudaMemcpy(P->d_fixtable, bc->fixtableU, n * sizeof(double), cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+int petiga_cuda_set_fixtable_device(petiga_cuda_plan* P, const double* table_own) {
+  if (!P) return PETIGA_CUDA_ERR_ARG;
+  PC_CUDA(cudaSetDevice(P->device));
+  PC_CUDA(cudaStreamSynchronize(P->stream));
+  cudaFree(P->d_fixtable);
+  P->d_fixtable = nullptr;
+  P->config_version++;
+  if (!table_own) return 0;
+  const Layout& L = P->L;
+  const size_t ng = L.localrow.size();
+  PC_CUDA(cudaMalloc(&P->d_fixtable, ng * L.dof * sizeof(double)));
+  const double* loc = table_own;          // one rank: local rows == owned rows
+  double* tmp = nullptr;
+  if (L.nranks > 1) {                     // ghost nodes carry their owner's table value (VecScatter g2l)
+    PC_CUDA(cudaMalloc(&tmp, (size_t)L.nloc * L.dof * sizeof(double)));
+    int rc = halo_state(P, table_own, tmp);
+    if (rc) { cudaFree(tmp); return rc; }
+    loc = tmp;
+  }
+  const int blocks = (int)std::min<size_t>((ng * L.dof + 255) / 256, (size_t)P->num_sms * 8);
+  fixtable_scatter_kernel<<<std::max(blocks, 1), 256, 0, P->stream>>>(P->d_localrow, loc, P->d_fixtable, ng, L.dof);
+  PC_CUDA(cudaGetLastError());
+  P->launches++;
+  PC_CUDA(cudaStreamSynchronize(P->stream));
+  cudaFree(tmp);
   return 0;
 }
 

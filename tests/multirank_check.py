@@ -84,6 +84,28 @@ def main():
                 print("%-20s %-10s path=%d %s%s" % (name, path, res["path"], "ok " if flag.item() == 0 else "FAIL", msg), flush=True)
             nfail += int(flag.item() != 0)
             g.Destroy()
+    # ---- IGASetFixTable on a distributed vector: G2L of the table over NCCL (test/IGAFixTable.c) ----
+    for name, case in [("fixtable 2d", Case(2, p=2, N=(12, 10), bcv=dall(2))), ("fixtable 3d dof2", Case(3, dof=2, p=2, N=6, bcv=[(0, 0, 0, 0.0), (1, 1, 1, 0.0), (2, 0, 0, 0.0)]))]:
+        o = case.oracle()
+        o.setup()
+        rp, ci, rs = o.pattern(world)
+        nn = len(rp) - 1
+        table = np.random.default_rng(21).standard_normal((nn, case.dof))
+        o.fixtable(table)
+        form = "POISSON" if case.dof == 1 else "MASS"
+        Ko, Fo = o.assemble("SYSTEM", form, [], size=world)
+        r0, r1 = int(rs[rank]), int(rs[rank + 1])
+        g = case.product(rank=rank, size=world, nccl=comm.value, device=local)
+        res = run_product(case, "SYSTEM", form, [], fixtable=table[r0:r1].reshape(-1), path="auto", g=g)
+        rpl = rp[r0:r1 + 1] - rp[r0]
+        eK = rel_frobenius(res["values"], oracle_to_layout(Ko[rp[r0]:rp[r1]], rpl, case.dof, res["baij"]))
+        eF = rel_frobenius(res["rhs"], Fo[r0:r1].reshape(-1))
+        flag = torch.tensor([0 if (eK <= 1e-12 and eF <= 1e-12) else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print("%-20s path=%d %s K=%.1e F=%.1e" % (name, res["path"], "ok " if flag.item() == 0 else "FAIL", eK, eF), flush=True)
+        nfail += int(flag.item() != 0)
+        g.Destroy()
     # ---- IGAComputeScalar / IGAComputeErrorNorm: state halo + ncclAllReduce (src/petigacomp.c:35-186) ----
     scalars = [
         ("errnorm 3d k=1", Case(3, dof=4, p=2, N=6, order=2), "ERRNORM", [1, 1, 0], 4),
