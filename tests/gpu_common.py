@@ -13,7 +13,8 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
         g.SetOption("quad_impl", quad_impl)
     if path is not None:
         g.SetOption("path", {"auto": 0, "quadrature": 1, "kronecker": 2}[path])
-    g.SetForm(slot, form, params)
+    # params are (lambda, mu) as the oracle takes them; the AppCtx of demo/Elasticity.c:10-13 is {mu, lambda}
+    g.SetForm(slot, form, [params[1], params[0]] if form == "ELASTICITY" else params)
     A = g.CreateMat() if slot in MAT_SLOTS else None
     B = g.CreateVec() if slot in VEC_SLOTS else None
     vU = vV = vT = None

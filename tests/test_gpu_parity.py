@@ -92,7 +92,8 @@ def test_elasticity_generic_with_load(dim, path):
     bcv = [(0, 0, i, 0.0) for i in range(dim)]
     bcl = [(0, 1, i, [1.0, 0.5, -0.25][i]) for i in range(dim)]
     case = Case(dim, dof=dim, p=2, N=5, order=1, bcv=bcv, bcl=bcl)
-    check_against_oracle(case, "SYSTEM", "ELASTICITY", params=[1.0, 1.0], path=path, tol=TOL)   # ctx {mu, lambda}
+    check_against_oracle(case, "SYSTEM", "ELASTICITY", params=[1.0, 1.0], path=path, tol=TOL)
+    check_against_oracle(case, "SYSTEM", "ELASTICITY", params=[2.0, 0.5], path=path, tol=TOL)   # lambda != mu: C is not symmetric in (al, be)
 
 
 # ---- F6 CahnHilliard2D (cfg 5 at reduced mesh): IFunction + IJacobian with state ---------------------------
@@ -184,6 +185,16 @@ def test_nurbs_quarter_annulus(form, params):
         g.SetForm("MATRIX", "MASS")
         g.ComputeMatrix(A)
         assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6
+
+
+# ---- large elements: 3-D p=3 dof=3 and p=4 dof 2-3 (only the sum-factorised kernel instantiates them) -----------------
+@pytest.mark.parametrize("p,dof,form,prm", [(3, 3, "ELASTICITY3D", [1.0, 1.0]), (4, 2, "MASS", []), (4, 3, "ELASTICITY", [2.0, 0.5])])
+def test_large_element_block_forms(p, dof, form, prm):
+    bcv = [(0, 0, c, 0.0) for c in range(dof)] + [(0, 1, 0, 1.0)]
+    case = Case(3, dof=dof, p=p, N=3, order=1, bcv=bcv)
+    check_against_oracle(case, "SYSTEM", form, prm, path="quadrature", tol=TOL)
+    case = Case(3, dof=dof, p=p, N=3, order=1, bcv=bcv, geometry=("perturbed", 0.05))
+    check_against_oracle(case, "SYSTEM", form, prm, path="quadrature", tol=TOL)
 
 
 # ---- Neumann loads on a mapped geometry: BoundaryArea integrates the surface Jacobian (petigaelem.c:1132-1162) ------
