@@ -74,6 +74,81 @@ __global__ void gather_owned_kernel(const double* __restrict__ src, double* __re
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// BoundaryArea of an element face on a mapped geometry: sum over the face's quadrature points of the surface Jacobian
+// sqrt|det(F F^T)|, F = d x / d(face parameters), times the weights (src/petigaelem.c:1132-1162 ->
+// IGA_BoundaryArea_{2,3}D, src/petiga{2,3}d.F90; Rationalize + Jacobian there).  The rationalised sums are folded:
+// F[r][s] = (Q[r][s] - S1[r] P[s] / W0) / W0 with W0 = sum W N0, S1 = sum W N1, P = sum W N0 X, Q = sum W N1 X.
+template <int DIM>
+__device__ double face_area_factor(const DevAxis* ax, const int* ID, int dir, int side, const double* __restrict__ X,
+                                          const double* __restrict__ Wt) {
+  if (DIM == 1) return 1.0;
+  int fa[2] = {0, 0}, n = 0;
+  for (int i = 0; i < DIM; i++) if (i != dir) fa[n++] = i;
+  const int sd = DIM - 1;
+  const DevAxis& A0 = ax[fa[0]];
+  const DevAxis& A1 = ax[(sd > 1) ? fa[1] : fa[0]];
+  const int ne0 = A0.nen, ne1 = (sd > 1) ? A1.nen : 1, nq0 = A0.nqp, nq1 = (sd > 1) ? A1.nqp : 1;
+  const int kfix = side ? ax[dir].nen - 1 : 0;
+  int g[3] = {0, 0, 0};
+  g[dir] = ax[dir].offset[ID[dir]] + kfix - ax[dir].gs;
+  const int b0 = A0.offset[ID[fa[0]]] - A0.gs, b1 = (sd > 1) ? A1.offset[ID[fa[1]]] - A1.gs : 0;
+  double dS = 0.0;
+  for (int jq = 0; jq < nq1; jq++)
+    for (int iq = 0; iq < nq0; iq++) {
+      double W0 = 0.0, S1[2] = {0, 0}, P[3] = {0, 0, 0}, Q[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      for (int ja = 0; ja < ne1; ja++) {
+        const double j0 = (sd > 1) ? A1.value[((size_t)(ID[fa[1]] * nq1 + jq) * ne1 + ja) * 5] : 1.0;
+        const double j1 = (sd > 1) ? A1.value[((size_t)(ID[fa[1]] * nq1 + jq) * ne1 + ja) * 5 + 1] : 0.0;
+        if (sd > 1) g[fa[1]] = b1 + ja;
+        for (int ia = 0; ia < ne0; ia++) {
+          const double i0 = A0.value[((size_t)(ID[fa[0]] * nq0 + iq) * ne0 + ia) * 5];
+          const double i1 = A0.value[((size_t)(ID[fa[0]] * nq0 + iq) * ne0 + ia) * 5 + 1];
+          g[fa[0]] = b0 + ia;
+          const int gidx = g[0] + ax[0].gw * (g[1] + ax[1].gw * g[2]);
+          const double w = Wt ? Wt[gidx] : 1.0;
+          const double N0 = w * i0 * j0, N1a = w * i1 * j0, N1b = w * i0 * j1;
+          W0 += N0; S1[0] += N1a; S1[1] += N1b;
+#pragma unroll
+          for (int s = 0; s < DIM; s++) {
+            const double x = X[(size_t)gidx * DIM + s];
+            P[s] = fma(N0, x, P[s]); Q[0][s] = fma(N1a, x, Q[0][s]); Q[1][s] = fma(N1b, x, Q[1][s]);
+          }
+        }
+      }
+      double F[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int s = 0; s < DIM; s++) F[r][s] = Wt ? (Q[r][s] - S1[r] * P[s] / W0) / W0 : Q[r][s];
+      double m00 = 0, m01 = 0, m11 = 0;
+#pragma unroll
+      for (int s = 0; s < DIM; s++) { m00 = fma(F[0][s], F[0][s], m00); m01 = fma(F[0][s], F[1][s], m01); m11 = fma(F[1][s], F[1][s], m11); }
+      const double det = (sd > 1) ? m00 * m11 - m01 * m01 : m00;
+      double wq = A0.weight[ID[fa[0]] * nq0 + iq];
+      if (sd > 1) wq *= A1.weight[ID[fa[1]] * nq1 + jq];
+      dS += sqrt(fabs(det)) * wq;
+    }
+  return dS;
+}
+
+
+struct FaceParams { DevAxis ax[3]; int dir, side, n0, n1; const double* X; const double* Wt; double* out; };
+
+// one thread per element of the face (dir, side) inside this rank's element box; kept out of the assembly kernels so that
+// the rare mapped-load case does not cost them registers (122 vs 77 in quad_sf_kernel<3,3,1,4> when it was inlined)
+template <int DIM>
+__global__ void face_area_kernel(const __grid_constant__ FaceParams fp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fp.n0 * fp.n1) return;
+  int fa[2] = {0, 0}, n = 0;
+  for (int i = 0; i < DIM; i++) if (i != fp.dir) fa[n++] = i;
+  int ID[3] = {0, 0, 0};
+  ID[fp.dir] = fp.side ? fp.ax[fp.dir].nel - 1 : 0;
+  ID[fa[0]] = fp.ax[fa[0]].es + t % fp.n0;
+  if (DIM > 2) ID[fa[1]] = fp.ax[fa[1]].es + t / fp.n0;
+  fp.out[t] = face_area_factor<DIM>(fp.ax, ID, fp.dir, fp.side, fp.X, fp.Wt);
+}
+
 // IGASetFixTable: local-row vector -> ghost-box table [ghost box][dof] (the G2L scatter of src/petigaform.c IGASetFixTable)
 __global__ void fixtable_scatter_kernel(const int* __restrict__ localrow, const double* __restrict__ loc, double* __restrict__ out, size_t ng, int dof) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ng * dof; i += (size_t)gridDim.x * blockDim.x) {
@@ -481,6 +556,30 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
           fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
         }
         if (fs.vcount || fs.lcount) kp.any_bc = 1;
+        if (fs.lcount && P->d_X && L.dim > 1 && !L.ax[d].periodic) {   // BoundaryArea on a mapped face (petigaelem.c:1132-1162)
+          int fa[2] = {0, 0}, nfa = 0;
+          for (int i = 0; i < L.dim; i++) if (i != d) fa[nfa++] = i;
+          const int n0 = L.ax[fa[0]].ew, n1 = (L.dim > 2) ? L.ax[fa[1]].ew : 1;
+          if (!P->d_face_dS[d][s]) {
+            void* buf = nullptr;
+            PC_CUDA(cudaMalloc(&buf, (size_t)n0 * n1 * sizeof(double)));
+            P->allocs.push_back(buf);
+            P->d_face_dS[d][s] = (double*)buf;
+            P->face_version[d][s] = -1;
+          }
+          if (P->face_version[d][s] != P->config_version) {
+            FaceParams fp;
+            for (int i = 0; i < 3; i++) fp.ax[i] = P->dax[i];
+            fp.dir = d; fp.side = s; fp.n0 = n0; fp.n1 = n1; fp.X = P->d_X; fp.Wt = P->d_W; fp.out = P->d_face_dS[d][s];
+            const int nb = (n0 * n1 + 127) / 128;
+            if (L.dim == 2) face_area_kernel<2><<<nb, 128, 0, P->stream>>>(fp);
+            else face_area_kernel<3><<<nb, 128, 0, P->stream>>>(fp);
+            PC_CUDA(cudaGetLastError());
+            P->launches++;
+            P->face_version[d][s] = P->config_version;
+          }
+          kp.face_dS[d][s] = P->d_face_dS[d][s];
+        }
       }
   kp.form = form; kp.slot = slot; kp.block = block;
   kp.mc0 = fi.mc0; kp.mc1 = quad_mat ? fi.mc1 : fi.mc0; kp.vc0 = fi.vc0; kp.vc1 = fi.vc1;

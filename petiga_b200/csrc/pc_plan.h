@@ -43,6 +43,8 @@ struct petiga_cuda_plan {
   double* d_X = nullptr;
   double* d_W = nullptr;
   double* d_fixtable = nullptr;
+  double* d_face_dS[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // BoundaryArea factors of mapped faces with loads
+  long face_version[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
   petiga_cuda_bc bc;
   bool has_bc = false;
   // unified local buffers (multi-rank) and exchange staging

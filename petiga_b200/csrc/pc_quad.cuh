@@ -141,7 +141,11 @@ quad_kernel(const __grid_constant__ KParams prm) {
               if (DIM > 1) {
                 for (int e = 0; e < DIM; e++)
                   if (e != d) A *= prm.ax[e].detJac[ID[e]] / (double)NEN1;
-                A *= mapped ? face_area_factor<DIM>(prm.ax, ID, d, s, prm.X, prm.Wt) : ((DIM == 2) ? 2.0 : 4.0);
+                if (prm.face_dS[d][s]) {   // mapped geometry: surface Jacobian integrated over the face (face_area_kernel, pc_api.cu)
+                  const int f0 = (d == 0) ? 1 : 0, f1 = (d == 2) ? 1 : 2;
+                  const int fidx = (ID[f0] - prm.ax[f0].es) + ((DIM > 2) ? prm.ax[f0].ew * (ID[f1] - prm.ax[f1].es) : 0);
+                  A *= prm.face_dS[d][s][fidx];
+                } else A *= (DIM == 2) ? 2.0 : 4.0;
               }
               for (int k = 0; k < fs.lcount; k++) vflux[fs.lfield[k]] += fs.lvalue[k] * A;
             }

@@ -141,3 +141,24 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(pb.IGAError) as e:
         g.CreateMat()
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_hot_kernel_register_budget():
+    """Occupancy guard (ptxas -v logs of the in-tree build): the sum-factorised kernel of cfg 2 must keep 3 CTAs of 256
+    threads per SM (<= 85 registers) and the separable kernel 4 (<= 64).  An inlined helper once pushed the former to 122
+    registers and cost 37 % at cfg 2 without failing any parity test."""
+    import os
+    import re
+    import petiga_b200
+    libdir = petiga_b200.lib_dir()
+
+    def regs(log, symbol_part):
+        txt = open(os.path.join(libdir, log)).read()
+        m = re.search(r"Compiling entry function '[^']*%s[^']*' for 'sm_100a'.*?Used (\d+) registers" % re.escape(symbol_part), txt, re.S)
+        assert m, symbol_part
+        return int(m.group(1))
+
+    if not os.path.exists(os.path.join(libdir, "pc_quad2.ptxas.log")):
+        pytest.skip("library not built in-tree")
+    assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4") <= 85
+    assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi1ELi3") <= 64
