@@ -148,12 +148,32 @@ def main_reference(args):
         "e2e": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (NCCL_DEBUG=VERSION on the GPU boxes) and other native libraries write
+    to fd 1 directly, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -375,7 +395,7 @@ def main():
         r = cpu_reference_run(1, 1, threads=1, per_rank=16)
         line["cpu_baseline"] = {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": 1, "kind": "port", "sample": r["sample"],
                                 "elements_per_s": r["elements_per_s"]}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
