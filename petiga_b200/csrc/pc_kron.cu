@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
   __shared__ int jkp1[kMaxWW];
   __shared__ double jkval[kMaxWW];
   __shared__ double Gm[2][kMaxWW];               // DOF == 1: G0/G3 with the Dirichlet (j,k) columns zeroed; Hs = sum over those columns of G*value
-  __shared__ double Hs[2];               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
+  __shared__ double Hs[2];
+  __shared__ int fast_ctr;                       // next 4-row pass of the interior stretch (dynamic hand-out)               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
   __shared__ double stage[(DOF > 1) ? 8 * 32 * DOF * DOF : 1];
   const int pencil = (int)blockIdx.x;
   const int Aj = kp.ls[1] + pencil % kp.lw[1], Ak = kp.ls[2] + pencil / kp.lw[1];
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
   const int fj = kp.first[1][Aj], fk = kp.first[2][Ak];
   const bool fixing = kp.any_bc && kp.slot == PETIGA_SLOT_SYSTEM;
   for (int t = threadIdx.x; t < 4 * DOF * DOF * kMaxWW; t += blockDim.x) (&G[0][0][0])[t] = 0.0;
+  if (threadIdx.x == 0) fast_ctr = 0;
   __syncthreads();
   bool jk_boundary = false;
   for (int t = threadIdx.x; t < Wjk; t += blockDim.x) {
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
   //      contribution to the right-hand side is separable:  -rowsum(M0^{00})*H0 - rowsum(M0^{11})*H3 ----
   int nfast = 0;
   const int fast_lo = kp.fast_lo;
+  bool pencil_fast = false;
   if (PF > 0) {
-    constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC, RW = WIC * WJKC, R = 4;
-    const bool pencil_fast = fast_ok && simple_jk && !(fixing && (rcj || rck)) && Wjk == WJKC && WiF == WIC && kp.fast_hi > fast_lo &&
-                             !(jk_boundary && (kp.fixtable || !want_vec));
+    constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC;
+    pencil_fast = fast_ok && simple_jk && !(fixing && (rcj || rck)) && Wjk == WJKC && WiF == WIC && kp.fast_hi > fast_lo &&
+                  !(jk_boundary && (kp.fixtable || !want_vec));
     if (pencil_fast) {
       if (jk_boundary) {   // uniform over the CTA
         if (warp == 0) {
@@ -242,42 +245,6 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
         __syncthreads();
       }
       nfast = kp.fast_hi - fast_lo;
-      const int64_t base_lo = __ldg(rowbase + lr0 + fast_lo);
-      const double* __restrict__ g0 = jk_boundary ? &Gm[0][grpF] : &G[0][0][grpF];
-      const double* __restrict__ g3 = jk_boundary ? &Gm[1][grpF] : &G[3][0][grpF];
-      const double H0 = jk_boundary ? Hs[0] : 0.0, H3 = jk_boundary ? Hs[1] : 0.0;
-      for (int il = fast_lo + warp * R; il < kp.fast_hi; il += nwarps * R) {
-        if (grpF < NGRP) {
-          double a0[R], a3[R];
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            a0[r] = __ldg(M0 + (size_t)(ls0 + il + r) * kMaxW + ciF);
-            a3[r] = __ldg(M0 + ((size_t)3 * nnp0 + ls0 + il + r) * kMaxW + ciF);
-          }
-          double* __restrict__ rowp = values + base_lo + (int64_t)(il - fast_lo) * RW + offF;
-#pragma unroll
-          for (int k = 0; k < NITER; k++)
-            if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) {
-              const double x0 = g0[k * NGRP], x3 = g3[k * NGRP];
-#pragma unroll
-              for (int r = 0; r < R; r++) rowp[r * RW + k * OSTEP] = fma(a3[r], x3, a0[r] * x0);
-            }
-        }
-        if (want_vec && lane < R) {
-          const int Ai = ls0 + il + lane;
-          double F;
-          if (vsimple) F = vjk * __ldg(mv0 + Ai);
-          else {
-            F = 0.0;
-            for (int n = 0; n < kp.nvterms; n++) {
-              const KronVTerm vt = kp.vterms[n];
-              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
-            }
-          }
-          if (jk_boundary) F -= __ldg(kp.rsum[0] + Ai) * H0 + __ldg(kp.rsum[0] + (size_t)3 * nnp0 + Ai) * H3;
-          rhs[lr0 + il + lane] = F;
-        }
-      }
     }
   }
   const int nslow = lw0 - nfast;   // the general loop walks the remaining rows (compacted index)
@@ -602,6 +569,52 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(cons
           if (rfix[c]) F = nelem * rval[c];
           kp.rhs[(size_t)lr * DOF + c] = F;
         }
+      }
+    }
+  }
+  // ---- the 4-row passes, handed out dynamically: warps that had a (slower) general row above join later, so the CTA's
+  //      warps finish together instead of leaving a low-parallelism tail ----
+  if (PF > 0 && pencil_fast) {
+    constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, NGRP = 32 / WIC, NITER = (WJKC + NGRP - 1) / NGRP, OSTEP = NGRP * WIC, RW = WIC * WJKC, R = 4;
+    const int64_t base_lo = __ldg(rowbase + lr0 + fast_lo);
+    const double* __restrict__ g0 = jk_boundary ? &Gm[0][grpF] : &G[0][0][grpF];
+    const double* __restrict__ g3 = jk_boundary ? &Gm[1][grpF] : &G[3][0][grpF];
+    const double H0 = jk_boundary ? Hs[0] : 0.0, H3 = jk_boundary ? Hs[1] : 0.0;
+    for (;;) {
+      int grab = 0;
+      if (lane == 0) grab = atomicAdd(&fast_ctr, 1);
+      grab = __shfl_sync(0xffffffffu, grab, 0);
+      const int il = fast_lo + grab * R;
+      if (il >= kp.fast_hi) break;
+      if (grpF < NGRP) {
+        double a0[R], a3[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          a0[r] = __ldg(M0 + (size_t)(ls0 + il + r) * kMaxW + ciF);
+          a3[r] = __ldg(M0 + ((size_t)3 * nnp0 + ls0 + il + r) * kMaxW + ciF);
+        }
+        double* __restrict__ rowp = values + base_lo + (int64_t)(il - fast_lo) * RW + offF;
+#pragma unroll
+        for (int k = 0; k < NITER; k++)
+          if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) {
+            const double x0 = g0[k * NGRP], x3 = g3[k * NGRP];
+#pragma unroll
+            for (int r = 0; r < R; r++) rowp[r * RW + k * OSTEP] = fma(a3[r], x3, a0[r] * x0);
+          }
+      }
+      if (want_vec && lane < R) {
+        const int Ai = ls0 + il + lane;
+        double F;
+        if (vsimple) F = vjk * __ldg(mv0 + Ai);
+        else {
+          F = 0.0;
+          for (int n = 0; n < kp.nvterms; n++) {
+            const KronVTerm vt = kp.vterms[n];
+            F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+          }
+        }
+        if (jk_boundary) F -= __ldg(kp.rsum[0] + Ai) * H0 + __ldg(kp.rsum[0] + (size_t)3 * nnp0 + Ai) * H3;
+        rhs[lr0 + il + lane] = F;
       }
     }
   }
