@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6)
-FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7)
+FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7,
+            BOUNDARYINTEGRAL=8, NEUMANN=9)
 SCALAR = dict(ERRNORM=0, CH_STATS=1)
 
 _dp = C.POINTER(C.c_double)
@@ -55,6 +56,8 @@ def lib(native=False):
     L.oiga_set_order.argtypes = [C.c_void_p, C.c_int]
     L.oiga_set_boundary_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
     L.oiga_set_boundary_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.oiga_set_boundary_form.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.oiga_tabulate_boundary.argtypes = [C.c_void_p, _ip, C.c_int, C.c_int, _ip] + [_dp] * 6
     L.oiga_set_geometry.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     L.oiga_set_fixtable.argtypes = [C.c_void_p, _dp, C.c_long]
     L.oiga_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -126,6 +129,22 @@ class OracleIGA:
 
     def boundary_load(self, axis, side, field, value):
         self.L.oiga_set_boundary_load(self.h, axis, side, field, value)
+
+    def boundary_form(self, axis, side, flag=True):
+        """IGASetBoundaryForm: visit the face with the boundary-integral pass (src/petigaelem.c:427-447)."""
+        self.L.oiga_set_boundary_form(self.h, axis, side, int(bool(flag)))
+
+    def tabulate_boundary(self, ID, axis, side):
+        inf = self.info()
+        nqp = int(np.prod([inf["nqp"][d] for d in range(self.dim) if d != axis])) if self.dim > 1 else 1
+        nen = int(np.prod(inf["nen"]))
+        o = dict(weight=np.zeros(nqp), detJac=np.zeros(nqp), detS=np.zeros(nqp), normal=np.zeros((nqp, self.dim)),
+                 X0=np.zeros((nqp, self.dim)), shape0=np.zeros((nqp, nen)))
+        ID3 = (C.c_int * 3)(*(list(ID) + [0, 0, 0])[:3])
+        q = C.c_int()
+        self.L.oiga_tabulate_boundary(self.h, ID3, axis, side, C.byref(q), *[_d(o[k]) for k in ("weight", "detJac", "detS", "normal", "X0", "shape0")])
+        assert q.value == nqp
+        return o
 
     def geometry(self, X, W=None):
         X = np.ascontiguousarray(X, dtype=np.float64)

@@ -43,6 +43,7 @@ typedef struct { /* include/petiga.h:50-60 */
 typedef struct { /* include/petiga.h:122-141 */
   int nel, nqp, nen;
   int *offset; double *detJac, *weight, *point, *value; /* value[nel][nqp][nen][5] */
+  double bnd_value[2][(MAXP+1)*5], bnd_point[2];        /* basis at the two ends of the axis (petigabasis.c:208-217) */
 } Basis;
 
 typedef struct { int count; int field[MAXBC]; double value[MAXBC]; } FormBC; /* petiga.h:221-225 */
@@ -53,6 +54,7 @@ typedef struct {
   int rule_nqp[3];
   Basis basis[3];
   FormBC value[3][2], load[3][2];
+  int visit[3][2];                                   /* IGASetBoundaryForm (petigaform.c): boundary-integral pass per face */
   /* geometry in natural (geom) ordering, i fastest: src/petigaio.c:201-286 */
   int geometry /* = nsd or 0 */, rational;
   double *geomX_nat, *geomW_nat;
@@ -73,7 +75,7 @@ typedef struct {
 
 enum { SLOT_VECTOR=0, SLOT_MATRIX, SLOT_SYSTEM, SLOT_FUNCTION, SLOT_JACOBIAN, SLOT_IFUNCTION, SLOT_IJACOBIAN };
 enum { FORM_POISSON=0, FORM_LAPLACE, FORM_L2PROJECTION, FORM_ELASTICITY3D, FORM_ELASTICITY,
-       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS };
+       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN };
 
 /* ------------------------------------------------------------------------------------------ */
 /* axis: src/petigaaxis.c                                                                     */
@@ -228,6 +230,17 @@ static int basis_init_quadrature(Basis *b, const Axis *ax, int nqp) /* petigabas
       double ders[MAXP+1][5];
       bspline_ders(kk, u[iqp], p, d, U, ders);
       for (a = 0; a < nen; a++) for (k = 0; k < 5; k++) N[(iqp*nen + a)*ndr + k] = ders[a][k];
+    }
+  }
+  { /* boundary tables: petigabasis.c:208-217 (k0 = p, u0 = U[k0]; k1 = n, u1 = U[k1+1]) */
+    int n = ax->m - p - 1, side; int kb[2]; double ub[2];
+    kb[0] = p; ub[0] = U[p]; kb[1] = n; ub[1] = U[n+1];
+    for (side = 0; side < 2; side++) {
+      double ders[MAXP+1][5];
+      memset(ders, 0, sizeof(ders));
+      bspline_ders(kb[side], ub[side], p, d, U, ders);
+      b->bnd_point[side] = ub[side];
+      for (a = 0; a < nen; a++) for (k = 0; k < 5; k++) b->bnd_value[side][a*ndr + k] = ders[a][k];
     }
   }
   return 0;
@@ -547,6 +560,8 @@ typedef struct {
   double *mapU[4], *mapX[4], *detX;      /* mapU[0]=point[nqp][dim]; mapU[k][nqp][dim][nsd^k]; mapX[k][nqp][nsd][dim^k] */
   int nfix, *ifix; double *vfix, *ufix; int nflux, *iflux; double *vflux;
   int geometry, rational;
+  int atboundary, baxis, bside;          /* boundary pass (petigaelem.c:427-447): face = (baxis, bside) */
+  double *normal, *detS;                 /* [nqp][nsd], [nqp] (petigaelem.c:1012-1022) */
 } Elem;
 
 static void elem_alloc(Elem *e, const OIGA *o)
@@ -561,6 +576,7 @@ static void elem_alloc(Elem *e, const OIGA *o)
   e->W = (double*)calloc((size_t)nen, sizeof(double)); e->X = (double*)calloc((size_t)nen*nsd, sizeof(double));
   e->weight = (double*)calloc((size_t)nqp, sizeof(double)); e->detJac = (double*)calloc((size_t)nqp, sizeof(double));
   e->detX = (double*)calloc((size_t)nqp, sizeof(double));
+  e->detS = (double*)calloc((size_t)nqp, sizeof(double)); e->normal = (double*)calloc((size_t)nqp*nsd, sizeof(double));
   for (k = 0; k < 4; k++) {
     e->basis[k] = (double*)calloc((size_t)nqp*nen*ipow(dim,k), sizeof(double));
     e->shape[k] = (double*)calloc((size_t)nqp*nen*ipow(nsd,k), sizeof(double));
@@ -574,7 +590,7 @@ static void elem_alloc(Elem *e, const OIGA *o)
 static void elem_free(Elem *e)
 {
   int k;
-  free(e->mapping); free(e->W); free(e->X); free(e->weight); free(e->detJac); free(e->detX);
+  free(e->mapping); free(e->W); free(e->X); free(e->weight); free(e->detJac); free(e->detX); free(e->detS); free(e->normal);
   for (k = 0; k < 4; k++) { free(e->basis[k]); free(e->shape[k]); free(e->mapU[k]); free(e->mapX[k]); }
   free(e->ifix); free(e->vfix); free(e->ufix); free(e->iflux); free(e->vflux);
 }
@@ -641,22 +657,27 @@ static void elem_tabulate(Elem *e)
   int dim = e->dim, nsd = e->nsd, nen = e->nen, ord = e->order;
   int NQ[3], i, q, a, k, nqp;
   const double *V[3];
+  const int bnd = e->atboundary, bax = e->baxis, bsd = e->bside;
   for (i = 0; i < 3; i++) {              /* IGA_Quadrature_SIZE: petigaelem.c:764-776 */
     const Basis *b = &o->basis[i]; int qq = b->nqp - 1; const double *w = b->weight + ID[i]*b->nqp;
     NQ[i] = 1; while (qq >= 0 && w[qq] <= 0) qq--; NQ[i] += qq;
     V[i] = b->value + (size_t)ID[i]*b->nqp*b->nen*5;
+    if (bnd && i == bax) { NQ[i] = 1; V[i] = b->bnd_value[bsd]; }   /* nqp /= NQ[axis]; NQ[axis] = 1 (:813-817); IGA_BasisFuns_BNDR :791 */
   }
   nqp = e->nqp = NQ[0]*NQ[1]*NQ[2];
   { /* IGA_Quadrature_3D: petiga3d.F90:1-29 */
     int iq, jq, kq; q = 0;
     double J = 1;
-    for (i = 0; i < dim; i++) J = (i == 0) ? o->basis[0].detJac[ID[0]] : J * o->basis[i].detJac[ID[i]];
+    for (i = 0; i < dim; i++) { double Ji = (bnd && i == bax) ? 1.0 : o->basis[i].detJac[ID[i]];   /* IGA_Quadrature_BNDR :788: bnd_detJac = 1 */
+      J = (i == 0) ? Ji : J * Ji; }
     for (kq = 0; kq < NQ[2]; kq++) for (jq = 0; jq < NQ[1]; jq++) for (iq = 0; iq < NQ[0]; iq++, q++) {
       int qi[3]; double w = 0; qi[0] = iq; qi[1] = jq; qi[2] = kq;
       for (i = 0; i < dim; i++) {
         const Basis *b = &o->basis[i];
-        e->mapU[0][q*dim + i] = b->point[ID[i]*b->nqp + qi[i]];
-        w = (i == 0) ? b->weight[ID[i]*b->nqp + qi[i]] : w * b->weight[ID[i]*b->nqp + qi[i]];
+        double pt = (bnd && i == bax) ? b->bnd_point[bsd] : b->point[ID[i]*b->nqp + qi[i]];
+        double wi = (bnd && i == bax) ? 1.0 : b->weight[ID[i]*b->nqp + qi[i]];                      /* bnd_weight = 1 */
+        e->mapU[0][q*dim + i] = pt;
+        w = (i == 0) ? wi : w * wi;
       }
       e->weight[q] = w; e->detJac[q] = J;
     }
@@ -798,6 +819,33 @@ static void elem_tabulate(Elem *e)
       }
     }
   }
+  if (bnd) {   /* normal and detS: petigaelem.c:1012-1022, IGA_GetNormal src/petigaval.F90:45-99 */
+    for (q = 0; q < nqp; q++) {
+      double *n = e->normal + (size_t)q*nsd; const double *F = e->mapX[1] + (size_t)q*nsd*dim;   /* F[i*dim+d] = dx_i/du_d */
+      if (e->geometry && dim == nsd) {
+        double dS = 1;
+        if (dim == 1) { n[0] = 1; }
+        else if (dim == 2) {   /* t = +F(2,:) (axis 0) or -F(1,:) (axis 1); N = (t2, -t1) */
+          double t[2]; int dd = (bax == 0) ? 1 : 0; double sg = (bax == 0) ? 1.0 : -1.0;
+          t[0] = sg*F[0*dim+dd]; t[1] = sg*F[1*dim+dd];
+          n[0] = +t[1]; n[1] = -t[0];
+          dS = sqrt(n[0]*n[0] + n[1]*n[1]); n[0] /= dS; n[1] /= dS;
+        } else {               /* s, t = rows (axis+1, axis+2) cyclic; N = s x t */
+          int ds = (bax+1)%3, dt = (bax+2)%3; double sv[3], tv[3];
+          for (i = 0; i < 3; i++) { sv[i] = F[i*dim+ds]; tv[i] = F[i*dim+dt]; }
+          n[0] = sv[1]*tv[2] - sv[2]*tv[1]; n[1] = sv[2]*tv[0] - sv[0]*tv[2]; n[2] = sv[0]*tv[1] - sv[1]*tv[0];
+          dS = sqrt(n[0]*n[0] + n[1]*n[1] + n[2]*n[2]); n[0] /= dS; n[1] /= dS; n[2] /= dS;
+        }
+        if (bsd == 0) for (i = 0; i < dim; i++) n[i] = -n[i];
+        e->detS[q] = dS;
+      } else {
+        for (i = 0; i < nsd; i++) n[i] = 0.0;
+        e->detS[q] = 1.0; n[bax] = bsd ? 1.0 : -1.0;
+      }
+    }
+    if (e->geometry) for (q = 0; q < nqp; q++) e->detJac[q] *= e->detS[q];   /* :1027-1028 */
+    return;
+  }
   for (q = 0; q < nqp; q++) e->detJac[q] *= e->detX[q];   /* petigaelem.c:1024-1029 */
 }
 
@@ -911,6 +959,7 @@ typedef struct { /* what a callback reads from IGAPoint: include/petiga.h:644-70
   int nen, dof, dim, nsd;
   const double *N0, *N1, *N2;  /* shape[0..2] of this point */
   const double *x;             /* mapX[0] (or mapU[0] when no geometry) */
+  int atboundary, boundary_id; const double *normal;   /* petiga.h:645-647,668 */
 } Point;
 
 static double l2_function(int choice, int dim, const double x[3]) /* demo/L2Projection.c:3-61 */
@@ -991,6 +1040,16 @@ static int form_system(int form, const double *prm, const Point *p, double *K, d
       F[a] = 0.0;
     }
 #undef KL
+    return 0; }
+  case FORM_BOUNDARYINTEGRAL: /* demo/BoundaryIntegral.c:27-57: Laplace in the interior, F = N*1.0 on the visited faces */
+    if (!p->atboundary) {
+      for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i]; K[a*nen+b] = sum; } F[a] = 0.0; }
+    } else for (a = 0; a < nen; a++) F[a] = p->N0[a] * 1.0;
+    return 0;
+  case FORM_NEUMANN: { /* demo/Neumann.c:5-45 SystemGalerkin: f = 4 pi^2 (sin 2 pi x + sin 2 pi y + sin 2 pi z) */
+    double xx[3] = {0,0,0}, f; for (i = 0; i < dim; i++) xx[i] = p->x[i];
+    f = 4*M_PI*M_PI * (sin(2*M_PI*xx[0]) + sin(2*M_PI*xx[1]) + sin(2*M_PI*xx[2]));
+    for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i]; K[a*nen+b] = sum; } F[a] = p->N0[a]*f; }
     return 0; }
   case FORM_ELASTICITY: { /* demo/Elasticity.c:22-52; dof == dim */
     double lambda = prm[0], mu = prm[1];
@@ -1170,10 +1229,18 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
           for (f = 0; f < e.nfix; f++) V[e.ifix[f]] = 0.0; }
         for (f = 0; f < e.nfix; f++) { e.ufix[f] = U[e.ifix[f]]; U[e.ifix[f]] = e.vfix[f]; }
       }
+      { int pass;   /* IGAElementNextForm (petigaelem.c:427-447): visited boundary faces of this element first, then the interior */
+      for (pass = 0; pass <= 2*e.dim && !err; pass++) {
+      if (pass < 2*e.dim) {
+        int bi = pass/2, bs = pass%2, be = bs ? o->elem_sizes[bi]-1 : 0;
+        if (e.ID[bi] != be || !o->visit[bi][bs]) continue;
+        e.atboundary = 1; e.baxis = bi; e.bside = bs;
+      } else e.atboundary = 0;
       elem_tabulate(&e);
       for (q = 0; q < e.nqp; q++) {      /* quadrature loop + IGAPointAddArray (petigapoint.c:451-465) */
         Point p; double JW = e.detJac[q] * e.weight[q]; int ret = 0;
         p.nen = e.nen; p.dof = dof; p.dim = e.dim; p.nsd = e.nsd;
+        p.atboundary = e.atboundary; p.boundary_id = e.atboundary ? 2*e.baxis + e.bside : -1; p.normal = e.normal + (size_t)q*e.nsd;
         p.N0 = e.shape[0] + (size_t)q*e.nen; p.N1 = e.shape[1] + (size_t)q*e.nen*e.nsd; p.N2 = e.shape[2] + (size_t)q*e.nen*e.nsd*e.nsd;
         p.x = e.geometry ? e.mapX[0] + (size_t)q*e.nsd : e.mapU[0] + (size_t)q*e.dim;
         if (want_mat) memset(K, 0, sizeof(double)*(size_t)N*N);
@@ -1193,6 +1260,7 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
         if (want_mat) for (i = 0; i < N*N; i++) A[i] += K[i] * JW;
         if (want_vec) for (i = 0; i < N; i++) B[i] += F[i] * JW;
       }
+      } e.atboundary = 0; }
       if (err) break;
       /* fix-up: petigaelem.c:1360-1389 (System), :1441-1463 (Function), :1483-1501 (Jacobian) */
       if (slot == SLOT_SYSTEM) {
@@ -1261,6 +1329,7 @@ void oiga_set_order(OIGA *o, int order) { o->order = order < 1 ? 1 : (order > 4 
 void oiga_set_boundary_value(OIGA *o, int axis, int side, int field, double v) /* petigaform.c:102-121 */
 { FormBC *bc = &o->value[axis][side]; int k; for (k = 0; k < bc->count; k++) if (bc->field[k] == field) break;
   if (k == bc->count) bc->count++; bc->field[k] = field; bc->value[k] = v; }
+void oiga_set_boundary_form(OIGA *o, int axis, int side, int flag) { o->visit[axis][side] = flag ? 1 : 0; }   /* petigaform.c IGAFormSetBoundaryForm */
 void oiga_set_boundary_load(OIGA *o, int axis, int side, int field, double v)
 { FormBC *bc = &o->load[axis][side]; int k; for (k = 0; k < bc->count; k++) if (bc->field[k] == field) break;
   if (k == bc->count) bc->count++; bc->field[k] = field; bc->value[k] = v; }
@@ -1356,6 +1425,8 @@ static int exact_eval(int id, int choice, int dim, int dof, const double *x, int
   }
   if (id == 2) { double xx[3] = {0,0,0}; if (k != 0) return 1; for (i = 0; i < dim; i++) xx[i] = x[i];
     for (c = 0; c < dof; c++) value[c] = l2_function(choice, dim, xx); return 0; }
+  if (id == 3) { double xx[3] = {0,0,0}; if (k != 0) return 1; for (i = 0; i < dim; i++) xx[i] = x[i];   /* demo/Neumann.c:5-8,80-86 Solution */
+    for (c = 0; c < dof; c++) value[c] = sin(2*M_PI*xx[0]) + sin(2*M_PI*xx[1]) + sin(2*M_PI*xx[2]); return 0; }
   return 1;
 }
 
@@ -1410,6 +1481,7 @@ int oiga_compute_scalar(OIGA *o, int size, int sid, const double *prm, const dou
         p.nen = e.nen; p.dof = dof; p.dim = e.dim; p.nsd = e.nsd;
         p.N0 = e.shape[0] + (size_t)q*e.nen; p.N1 = e.shape[1] + (size_t)q*e.nen*e.nsd; p.N2 = e.shape[2] + (size_t)q*e.nen*e.nsd*e.nsd;
         p.x = e.geometry ? e.mapX[0] + (size_t)q*e.nsd : e.mapU[0] + (size_t)q*e.dim;
+        p.atboundary = 0; p.boundary_id = -1; p.normal = NULL;
         memset(workS, 0, sizeof(double)*(size_t)n);
         if (scalar_point(sid, prm, &p, U, n, workS, w0, w1)) { err = 10; break; }
         for (i = 0; i < n; i++) localS[(size_t)r*n+i] += workS[i] * JW;    /* IGAPointAddArray (petigapoint.c:451-465) */
@@ -1421,6 +1493,27 @@ int oiga_compute_scalar(OIGA *o, int size, int sid, const double *prm, const dou
   for (i = 0; i < n; i++) { S[i] = 0; for (r = 0; r < size; r++) S[i] += localS[(size_t)r*n+i]; }
   free(localS); free(workS);
   return err;
+}
+
+/* Boundary tabulation of one element face (after oiga_setup): out arrays [nqp_face]: detJac (already *detS), detS, normal[..][nsd],
+   X0[..][nsd], shape0[..][nen] -- for the known answers of test/IGAGeometryMap.c:275-389 */
+int oiga_tabulate_boundary(OIGA *o, const int ID[3], int axis, int side, int *nqp, double *weight, double *detJac, double *detS,
+                           double *normal, double *X0, double *shape0)
+{
+  Elem e; int k;
+  elem_alloc(&e, o);
+  for (k = 0; k < 3; k++) e.ID[k] = ID[k];
+  e.atboundary = 1; e.baxis = axis; e.bside = side;
+  elem_closure(&e); elem_tabulate(&e);
+  *nqp = e.nqp;
+  if (weight) memcpy(weight, e.weight, sizeof(double)*e.nqp);
+  if (detJac) memcpy(detJac, e.detJac, sizeof(double)*e.nqp);
+  if (detS)   memcpy(detS, e.detS, sizeof(double)*e.nqp);
+  if (normal) memcpy(normal, e.normal, sizeof(double)*e.nqp*e.nsd);
+  if (X0) memcpy(X0, e.geometry ? e.mapX[0] : e.mapU[0], sizeof(double)*e.nqp*e.nsd);
+  if (shape0) memcpy(shape0, e.shape[0], sizeof(double)*e.nqp*e.nen);
+  elem_free(&e);
+  return 0;
 }
 
 /* Tabulate one element of the current rank (after oiga_setup) for the geometry known-answer tests.
