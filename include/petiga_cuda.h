@@ -70,14 +70,18 @@ enum {
   PETIGA_FORM_CAHNHILLIARD2D = 5, /* demo/CahnHilliard2D.c:84-197 Residual/Tangent; params = {theta, alpha}         */
   PETIGA_FORM_BRATU = 6,          /* demo/BratuFJ.F90 Function/Jacobian/IFunction/IJacobian; params = {lambda}      */
   PETIGA_FORM_MASS = 7,           /* test/IGACreate.c:10-64 Vector/Matrix/System (block mass, any dof)              */
-  PETIGA_NFORMS = 8
+  PETIGA_FORM_BOUNDARYINTEGRAL = 8, /* demo/BoundaryIntegral.c:27-57 System: Laplace inside, F = N*1.0 on the faces
+                                     enabled with petiga_cuda_set_boundary_form (p->atboundary branch)               */
+  PETIGA_FORM_NEUMANN = 9,        /* demo/Neumann.c:28-45 SystemGalerkin: Laplace + f = 4 pi^2 sum_i sin(2 pi x_i)   */
+  PETIGA_NFORMS = 10
 };
 
 /* built-in Scalar callbacks of petiga_cuda_compute_scalar (IGAComputeScalar, src/petigacomp.c:35-96) */
 enum {
   PETIGA_SCALAR_ERRNORM = 0,      /* ErrorSqr of IGAComputeErrorNorm (src/petigacomp.c:103-124): n = dof squared errors;
                                      params = {k (0..2), exact id, choice}; exact id 0 = NULL, 1 = test/IGAErrNorm.c:26-52
-                                     (dof 4), 2 = demo/L2Projection.c:3-61 function `choice` (k = 0)                      */
+                                     (dof 4), 2 = demo/L2Projection.c:3-61 function `choice` (k = 0), 3 = demo/Neumann.c:5-8
+                                     Solution (k = 0)                                                                      */
   PETIGA_SCALAR_CH_STATS = 1,     /* demo/CahnHilliard2D.c:36-58 monitor: n = 3 (free energy, 2nd, 3rd moment);
                                      params = {theta, alpha, cbar}                                                          */
   PETIGA_NSCALARS = 2
@@ -140,6 +144,14 @@ int petiga_cuda_get_stat(petiga_cuda_plan *plan, const char *name, double *value
    nsd must equal dim.  Pass X == NULL to return to the identity map. */
 int petiga_cuda_set_geometry(petiga_cuda_plan *plan, int nsd, const double *X, const double *W);
 int petiga_cuda_set_bc(petiga_cuda_plan *plan, const petiga_cuda_bc *bc);
+/* Boundary-integral pass (IGASetBoundaryForm, src/petigaform.c; element side src/petigaelem.c:427-447,813-868,1012-1029):
+   set_boundary_tables hands over IGABasis.bnd_value[0..1] ([p+1][5] each) and bnd_point[0..1] of one axis
+   (include/petiga.h:134-139, src/petigabasis.c:208-217); set_boundary_form switches the pass on for a face.  A form
+   without a boundary term (everything except PETIGA_FORM_BOUNDARYINTEGRAL) makes petiga_cuda_compute return
+   PETIGA_CUDA_ERR_SUP while a face is enabled. */
+int petiga_cuda_set_boundary_tables(petiga_cuda_plan *plan, int axis, const double *bnd_value0, const double *bnd_value1,
+                                    double bnd_point0, double bnd_point1);
+int petiga_cuda_set_boundary_form(petiga_cuda_plan *plan, int axis, int side, int flag);
 /* IGASetFixTable with the table as a *global device vector* (this rank's owned part [owned nodes * dof]): the library does
    the global-to-local scatter itself (NCCL halo on more than one rank).  Call after petiga_cuda_set_bc; NULL clears it. */
 int petiga_cuda_set_fixtable_device(petiga_cuda_plan *plan, const double *table_own);

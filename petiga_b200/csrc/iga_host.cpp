@@ -74,6 +74,8 @@ struct _p_IGA {
   petiga_cuda_plan* plan = nullptr;
   void* stream = nullptr;
   std::vector<std::pair<std::string, double>> options;
+  int visit[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // IGASetBoundaryForm
+  std::vector<double> bnd_value[3][2]; double bnd_point[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // IGABasis.bnd_* (petigabasis.c:208-217)
   bool async = false;   // IGASetOption("async",1): the drivers only enqueue; IGASynchronize / host getters wait
 };
 
@@ -202,6 +204,11 @@ PetscErrorCode ensure_plan(IGA g) {
     g->bc_dirty = g->geom_dirty = true;
     for (auto& s : g->slots) s.dirty = (s.form >= 0);
     for (auto& o : g->options) { rc = petiga_cuda_set_option(g->plan, o.first.c_str(), o.second); if (rc) return from_cuda(rc); }
+    for (int d = 0; d < g->dim; d++) {
+      rc = petiga_cuda_set_boundary_tables(g->plan, d, g->bnd_value[d][0].data(), g->bnd_value[d][1].data(), g->bnd_point[d][0], g->bnd_point[d][1]);
+      if (rc) return from_cuda(rc);
+      for (int sd = 0; sd < 2; sd++) { rc = petiga_cuda_set_boundary_form(g->plan, d, sd, g->visit[d][sd]); if (rc) return from_cuda(rc); }
+    }
   }
   if (g->geom_dirty) {
     if (g->nsd) {   // ghost-box slice of the natural arrays (src/petigaio.c:255-286)
@@ -254,6 +261,8 @@ const FormEntry* lookup_form(const void* fn, int slot) {
       {FN(IGADeviceForm_Laplace_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_LAPLACE, 0, 0},
       {FN(IGADeviceForm_L2Projection_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_L2PROJECTION, 1, 0},
       {FN(IGADeviceForm_Mass_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_MASS, 0, 0},
+      {FN(IGADeviceForm_BoundaryIntegral_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_BOUNDARYINTEGRAL, 0, 0},
+      {FN(IGADeviceForm_Neumann_SystemGalerkin), PETIGA_SLOT_SYSTEM, PETIGA_FORM_NEUMANN, 0, 0},
       {FN(IGADeviceForm_Mass_Matrix), PETIGA_SLOT_MATRIX, PETIGA_FORM_MASS, 0, 0},
       {FN(IGADeviceForm_Mass_Vector), PETIGA_SLOT_VECTOR, PETIGA_FORM_MASS, 0, 0},
       {FN(IGADeviceForm_Elasticity3D_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_ELASTICITY3D, 2, 0},
@@ -298,6 +307,8 @@ const char* IGAGetLastErrorMessage(void) { return g_msg.c_str(); }
 SENT4(IGADeviceForm_Poisson_System) SENTF(IGADeviceForm_Poisson_Function) SENTF(IGADeviceForm_Poisson_Jacobian)
 SENT4(IGADeviceForm_Laplace_System) SENT4(IGADeviceForm_L2Projection_System) SENT4(IGADeviceForm_Mass_System)
 SENT3(IGADeviceForm_Mass_Matrix) SENT3(IGADeviceForm_Mass_Vector)
+SENT4(IGADeviceForm_BoundaryIntegral_System) SENT4(IGADeviceForm_Neumann_SystemGalerkin)
+PetscErrorCode IGADeviceExact_Neumann(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 SENT4(IGADeviceForm_Elasticity3D_System) SENT4(IGADeviceForm_Elasticity_System)
 SENTI(IGADeviceForm_CahnHilliard2D_Residual) SENTI(IGADeviceForm_CahnHilliard2D_Tangent)
 PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar*, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
@@ -513,6 +524,20 @@ PetscErrorCode IGASetUp(IGA g) {
       }
     }
   }
+  for (int d = 0; d < 3; d++) {   // boundary tables: k0 = p, u0 = U[k0]; k1 = n, u1 = U[k1+1] (src/petigabasis.c:208-217)
+    const _n_IGAAxis& ax = g->axis[d];
+    const int p = ax.p, n = ax.m - p - 1, nd = std::min(p, 4);
+    const int kb[2] = {p, n};
+    const double ub[2] = {ax.U[p], ax.U[n + 1]};
+    for (int s = 0; s < 2; s++) {
+      double ders[9][5];
+      memset(ders, 0, sizeof(ders));
+      bspline_ders(kb[s], ub[s], p, nd, ax.U.data(), ders);
+      g->bnd_value[d][s].assign((size_t)(p + 1) * 5, 0.0);
+      for (int a = 0; a <= p; a++) for (int dd = 0; dd < 5; dd++) g->bnd_value[d][s][(size_t)a * 5 + dd] = ders[a][dd];
+      g->bnd_point[d][s] = ub[s];
+    }
+  }
   if (g->layout) { petiga_layout_destroy(g->layout); g->layout = nullptr; }
   petiga_cuda_space sp;
   fill_space(g, sp);
@@ -568,6 +593,17 @@ static PetscErrorCode set_bc_entry(IGA g, PetscInt axis, PetscInt side, PetscInt
 }
 PetscErrorCode IGASetBoundaryValue(IGA g, PetscInt a, PetscInt s, PetscInt f, PetscScalar v) { return set_bc_entry(g, a, s, f, v, false); }
 PetscErrorCode IGASetBoundaryLoad(IGA g, PetscInt a, PetscInt s, PetscInt f, PetscScalar v) { return set_bc_entry(g, a, s, f, v, true); }
+// include/petiga.h:300, src/petigaform.c IGAFormSetBoundaryForm
+PetscErrorCode IGASetBoundaryForm(IGA g, PetscInt axis, PetscInt side, PetscBool flag) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (axis < 0) return fail(PETSC_ERR_ARG_OUTOFRANGE, "axis must be nonnegative");
+  if (axis >= 3) return fail(PETSC_ERR_ARG_OUTOFRANGE, "axis must be less than 3");
+  if (side < 0) return fail(PETSC_ERR_ARG_OUTOFRANGE, "side must be nonnegative");
+  if (side >= 2) return fail(PETSC_ERR_ARG_OUTOFRANGE, "side must be less than 2");
+  g->visit[axis][side] = flag ? 1 : 0;
+  if (g->plan) return from_cuda(petiga_cuda_set_boundary_form(g->plan, axis, side, g->visit[axis][side]));
+  return 0;
+}
 PetscErrorCode IGASetFixTable(IGA g, Vec table) { if (PetscErrorCode e = check(g)) return e; g->fixtable = table; g->bc_dirty = true; return 0; }
 
 PetscErrorCode IGASetFormVector(IGA g, IGAFormVector f, void* ctx) { return set_form(g, PETIGA_SLOT_VECTOR, (const void*)f, ctx); }
@@ -681,6 +717,7 @@ PetscErrorCode IGAComputeErrorNorm(IGA g, PetscInt k, Vec vecU, IGAFormExact Exa
   if (k < 0) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Derivative index must be nonnegative");   // :170
   double prm[3] = {(double)k, 0.0, 0.0};
   if (Exact == IGADeviceExact_ErrNormTest) prm[1] = 1;
+  else if (Exact == IGADeviceExact_Neumann) prm[1] = 3;
   else if (Exact == IGADeviceExact_L2Projection) { prm[1] = 2; if (!ctx) return fail(PETSC_ERR_ARG_NULL, "IGADeviceExact_L2Projection needs {choice}"); prm[2] = *(const double*)ctx; }
   else if (Exact) return fail(PETSC_ERR_SUP, "IGAComputeErrorNorm: host callbacks cannot run on the GPU; pass one of the IGADeviceExact_* sentinels or NULL");
   if (PetscErrorCode e = ensure_plan(g)) return e;

@@ -492,8 +492,13 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   const size_t nval = (size_t)L.nnz_own * bs2, nvec = (size_t)L.nown * L.dof;
   const bool multi = L.nranks > 1;
 
+  // boundary-integral pass (IGASetBoundaryForm): which faces are visited, and does the form have a face term?
+  bool any_visit = false;
+  for (int d = 0; d < L.dim; d++) for (int s = 0; s < 2; s++) if (P->visit[d][s] && !L.ax[d].periodic) any_visit = true;
+  if (any_visit && !form_has_boundary_term(form)) { set_error("compute: a face is enabled with IGASetBoundaryForm but this built-in form has no boundary term"); return PETIGA_CUDA_ERR_SUP; }
+  const bool bnd_pass = any_visit && want_vec;
   // path selection
-  const bool kron_ok = kron_applicable(P, slot, form);
+  const bool kron_ok = kron_applicable(P, slot, form) && !bnd_pass;
   if (P->path == PETIGA_PATH_KRONECKER && !kron_ok) { set_error("compute: separable path not applicable (geometry, state or non-separable form)"); return PETIGA_CUDA_ERR_SUP; }
   const bool use_kron = kron_ok && P->path != PETIGA_PATH_QUADRATURE;
   P->last_path = use_kron ? PETIGA_PATH_KRONECKER : PETIGA_PATH_QUADRATURE;
@@ -601,6 +606,10 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   if (rc == PETIGA_CUDA_ERR_SUP && P->quad_impl < 0) rc = impl == 1 ? launch_quadrature_sf(P, kp) : launch_quadrature(P, kp);
   if (rc) return rc;
   P->last_impl = impl;
+  if (bnd_pass) {   // face terms go into the same (unified local) vector, before the ghost-row exchange
+    rc = launch_boundary_pass(P, slot, form, P->slots[slot].prm, rhs_k, apply_bc && P->has_bc);
+    if (rc) return rc;
+  }
   cudaEventRecord(P->ev1, P->stream);
   if (multi) {
     rc = exchange_ghost_rows(P, block, values, rhs, quad_mat, want_vec);

@@ -43,6 +43,9 @@ struct petiga_cuda_plan {
   double* d_X = nullptr;
   double* d_W = nullptr;
   double* d_fixtable = nullptr;
+  double* d_bnd_value[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // IGABasis.bnd_value on the device
+  double bnd_point[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  int visit[3][2] = {{0, 0}, {0, 0}, {0, 0}};            // IGASetBoundaryForm flags
   double* d_face_dS[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // BoundaryArea factors of mapped faces with loads
   long face_version[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
   petiga_cuda_bc bc;
@@ -98,4 +101,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
 int exchange_ghost_rows(petiga_cuda_plan* P, int block, double* values, double* rhs, bool mat, bool vec);
 int halo_state(petiga_cuda_plan* P, const double* U_own, double* U_loc);
 int nccl_load();
+// boundary-integral pass (pc_bnd.cu)
+bool form_has_boundary_term(int form);
+int launch_boundary_pass(petiga_cuda_plan* P, int slot, int form, const double* prm, double* rhs, bool apply_fix);
 }  // namespace pc

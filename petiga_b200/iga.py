@@ -17,6 +17,8 @@ FORMS = {
                 "JACOBIAN": "IGADeviceForm_Poisson_Jacobian"},
     "LAPLACE": {"SYSTEM": "IGADeviceForm_Laplace_System"},
     "L2PROJECTION": {"SYSTEM": "IGADeviceForm_L2Projection_System"},
+    "BOUNDARYINTEGRAL": {"SYSTEM": "IGADeviceForm_BoundaryIntegral_System"},
+    "NEUMANN": {"SYSTEM": "IGADeviceForm_Neumann_SystemGalerkin"},
     "MASS": {"SYSTEM": "IGADeviceForm_Mass_System", "MATRIX": "IGADeviceForm_Mass_Matrix", "VECTOR": "IGADeviceForm_Mass_Vector"},
     "ELASTICITY3D": {"SYSTEM": "IGADeviceForm_Elasticity3D_System"},
     "ELASTICITY": {"SYSTEM": "IGADeviceForm_Elasticity_System"},
@@ -236,6 +238,9 @@ class IGA:
 
     def SetBoundaryLoad(self, axis, side, field, value):
         _chk(self.H.IGASetBoundaryLoad(self.h, axis, side, field, C.c_double(value)))
+
+    def SetBoundaryForm(self, axis, side, flag=True):
+        _chk(self.H.IGASetBoundaryForm(self.h, axis, side, int(bool(flag))))
 
     def SetFixTable(self, vec):
         _chk(self.H.IGASetFixTable(self.h, vec.h if vec is not None else None))

@@ -12,9 +12,10 @@ class Case:
     """One discretisation + BC + form configuration, applicable to both the oracle and the product."""
 
     def __init__(self, dim, dof=1, p=2, N=8, C=-1, periodic=False, limits=(0.0, 1.0), q=None, order=None,
-                 bcv=(), bcl=(), geometry=None, mattype=None, name=""):
+                 bcv=(), bcl=(), bcf=(), geometry=None, mattype=None, name=""):
         self.dim, self.dof, self.p, self.N, self.C, self.periodic = dim, dof, p, N, C, periodic
         self.limits, self.q, self.order, self.bcv, self.bcl = limits, q, order, list(bcv), list(bcl)
+        self.bcf = list(bcf)          # faces (axis, side) visited by the boundary-integral pass (IGASetBoundaryForm)
         self.geometry = geometry      # None | ("perturbed", amp) | ("arrays", X, W)
         self.mattype = mattype
         self.name = name
@@ -28,7 +29,7 @@ class Case:
             return perturbed_identity(self.dim, self.p, [_per_axis(self.N, d) for d in range(self.dim)], self.geometry[1]), None
         return self.geometry[1], self.geometry[2]
 
-    def _apply(self, o, uniform, rule, order, bv, bl, geom):
+    def _apply(self, o, uniform, rule, order, bv, bl, geom, bf=None):
         for d in range(self.dim):
             uniform(d, _per_axis(self.p, d), _per_axis(self.N, d), self.limits[0], self.limits[1], _per_axis(self.C, d),
                     bool(_per_axis(self.periodic, d)))
@@ -40,19 +41,22 @@ class Case:
             bv(a, s, f, v)
         for (a, s, f, v) in self.bcl:
             bl(a, s, f, v)
+        for (a, s) in self.bcf:
+            bf(a, s, True)
         X, W = self.geometry_arrays()
         if X is not None:
             geom(X, W)
 
     def oracle(self, native=False):
         o = OracleIGA(self.dim, self.dof, native=native)
-        self._apply(o, o.axis_uniform, o.rule_size, o.order, o.boundary_value, o.boundary_load, o.geometry)
+        self._apply(o, o.axis_uniform, o.rule_size, o.order, o.boundary_value, o.boundary_load, o.geometry, o.boundary_form)
         return o
 
     def product(self, rank=0, size=1, nccl=None, device=0, setup=True):
         import petiga_b200 as pb
         g = pb.IGA(self.dim, self.dof, rank=rank, size=size, nccl=nccl, device=device)
-        self._apply(g, g.AxisInitUniform, g.SetRuleSize, g.SetOrder, g.SetBoundaryValue, g.SetBoundaryLoad, g.SetGeometryArrays)
+        self._apply(g, g.AxisInitUniform, g.SetRuleSize, g.SetOrder, g.SetBoundaryValue, g.SetBoundaryLoad, g.SetGeometryArrays,
+                    g.SetBoundaryForm)
         if self.mattype:
             g.SetMatType(self.mattype)
         if setup:

@@ -43,6 +43,9 @@ def main():
         ("elasticity3d aij", Case(3, dof=3, p=2, N=6, mattype="aij", bcv=[(0, 0, 0, 0.0), (0, 1, 0, 1.0)]), "SYSTEM", "ELASTICITY3D", [1.0, 1.0], False),
         ("mass periodic dof2", Case(2, dof=2, p=2, N=(24, 20), periodic=(True, False)), "SYSTEM", "MASS", [], False),
         ("mapped poisson", Case(3, p=2, N=8, geometry=("perturbed", 0.05), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("boundary integral", Case(3, p=2, N=6, bcv=[(0, 0, 0, 1.0)], bcf=[(d, s) for d in range(3) for s in range(2)]), "SYSTEM", "BOUNDARYINTEGRAL", [], False),
+        ("boundary int mapped", Case(2, p=3, N=(9, 8), geometry=("perturbed", 0.05), bcv=[(1, 0, 0, 1.0)], bcf=[(0, 0), (0, 1), (1, 1)]), "SYSTEM", "BOUNDARYINTEGRAL", [], False),
+        ("neumann demo", Case(2, p=2, N=(12, 10), bcl=[(d, s, 0, (2 * s - 1) * 6.283185307179586) for d in range(2) for s in range(2)]), "SYSTEM", "NEUMANN", [], False),
         ("cahnhilliard IJ", Case(2, p=2, N=32, C=1, periodic=True), "IJACOBIAN", "CAHNHILLIARD2D", [1.5, 3000.0], True),
         ("cahnhilliard IF", Case(2, p=2, N=32, C=1, periodic=True), "IFUNCTION", "CAHNHILLIARD2D", [1.5, 3000.0], True),
         ("bratu F", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "FUNCTION", "BRATU", [6.8], True),
