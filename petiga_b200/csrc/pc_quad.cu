@@ -23,7 +23,7 @@ int launch_one(petiga_cuda_plan* Pl, KParams prm) {
   // pick the chunk size and the elements per block so that two CTAs fit an SM when possible
   const size_t budget = 100 * 1024, hard = 220 * 1024;
   int qc = std::min(nqp, 32), epb = std::max(1, 256 / G);
-  auto bytes = [&](int q, int e) { return (size_t)QSmem(Cfg::M, Cfg::N, DIM, DOF, NC, NA, NV, q, Cfg::NEN1).total * 8 * e; };
+  auto bytes = [&](int q, int e) { return (size_t)QSmem(Cfg::M, Cfg::N, DIM, DOF, NC, NA, NV, q, Cfg::NEN1, G).total * 8 * e; };
   while (qc > 1 && bytes(qc, epb) > budget) qc = (qc + 1) / 2;
   while (epb > 1 && bytes(qc, epb) > budget) epb--;
   if (bytes(qc, epb) > hard) { set_error("quadrature kernel: element does not fit shared memory"); return PETIGA_CUDA_ERR_SUP; }

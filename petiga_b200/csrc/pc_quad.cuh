@@ -36,7 +36,7 @@ struct QCfg {
 // shared-memory carve-up of one element slot (offsets in doubles); identical on host and device
 struct QSmem {
   int psi, bs, cq, fq, jw, geo, xq, sq, fe, ue, ve, xe, we, fixval, flux, ufix, ints, total;
-  __host__ __device__ QSmem(int M, int N, int dim, int dof, int NC, int NA, int NV, int QC, int nen1) {
+  __host__ __device__ QSmem(int M, int N, int dim, int dof, int NC, int NA, int NV, int QC, int nen1, int G = 0) {
     int o = 0;
     psi = o; o += QC * NC * M;
     bs = o; o += QC * NA * N;
@@ -56,6 +56,10 @@ struct QSmem {
     ufix = o; o += M * dof;
     ints = o; o += (M + M * dof + 3 * nen1 * nen1 + 3 * nen1 + 8 + 1) / 2 + 1;   // lrow, fixflag, segs, Wd, ID
     total = o;
+    // several small elements share a CTA, G threads each: with a slot stride = G (mod 16 doubles) the threads of a warp that
+    // belong to consecutive elements hit consecutive banks, as if the per-element arrays were packed back to back
+    // (ncu r1_ncu_quad_kernel_cfg5: the T-builder's loads/stores ran at 2x their ideal wavefronts with the unpadded stride)
+    if (G > 0 && G < 32) while (total % 16 != G % 16) total++;
   }
 };
 
@@ -68,7 +72,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
   constexpr int NEN1 = Cfg::NEN1, M = Cfg::M, N = Cfg::N, TN = Cfg::TN, GN = Cfg::GN, G = Cfg::G;
   extern __shared__ double smem_all[];
   const int NC = prm.c1 - prm.c0, NA = prm.mc1 - prm.mc0, NV = prm.vc1 - prm.vc0, QC = prm.qc;
-  const QSmem lay(M, N, DIM, DOF, NC, NA, NV, QC, NEN1);
+  const QSmem lay(M, N, DIM, DOF, NC, NA, NV, QC, NEN1, G);
   const int grp = threadIdx.x / G, lt = threadIdx.x - grp * G;
   const bool ingrp = grp < prm.epb;
   const int elem = blockIdx.x * prm.epb + grp;
