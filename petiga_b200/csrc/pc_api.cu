@@ -598,6 +598,7 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   kp.c0 = c0; kp.c1 = c1;
   memcpy(kp.prm, P->slots[slot].prm, sizeof(kp.prm));
   kp.shift = shift; kp.t = t;
+  kp.noscatter = (P->scatter == 99);
   // kernel choice (measured, profiles/r1_configs_1gpu.jsonl): the sum-factorised kernel wins on large elements (3-D, p >= 2:
   // 6x at cfg 2), the pair-loop kernel on small ones where per-element set-up dominates (5x at cfg 5, 2-D p=2)
   int impl = P->quad_impl;

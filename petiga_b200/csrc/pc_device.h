@@ -56,6 +56,7 @@ struct KParams {
   double shift, t;
   int qc;                          // quadrature points per chunk
   int epb;                         // elements per block
+  int noscatter;                   // profiling only (set_option "scatter" = 99): integrate but skip the global reductions
 };
 
 }  // namespace pc

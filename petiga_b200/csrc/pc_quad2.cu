@@ -157,15 +157,21 @@ int launch_sf_nq(petiga_cuda_plan* Pl, SFParams& sp) {
   sp.k.epb = epb;
   const size_t smem = per * epb;
   const int threads = ((Cfg::G * epb + 31) / 32) * 32;
-  auto kern = quad_sf_kernel<DIM, P, DOF, NQ>;
-  PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the 64-register build only where it can run 4 CTAs per SM: one full-CTA element, default rule, four slots fit
+  constexpr bool kHas4 = (Cfg::THREADS == 256 && Cfg::G == 256 && DOF == 1 && NQ > 0);
+  const bool use4 = kHas4 && epb == 1 && (smem + 1024) * 4 <= 227 * 1024;
   const int blocks = (base.nelem + epb - 1) / epb;
-  if (blocks > 0) {
-    kern<<<blocks, threads, smem, Pl->stream>>>(sp);
-    PC_CUDA(cudaGetLastError());
-    Pl->launches++;
-  }
-  return 0;
+  auto go = [&](auto kern) -> int {
+    PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (blocks > 0) {
+      kern<<<blocks, threads, smem, Pl->stream>>>(sp);
+      PC_CUDA(cudaGetLastError());
+      Pl->launches++;
+    }
+    return 0;
+  };
+  if constexpr (kHas4) { if (use4) return go(quad_sf_kernel<DIM, P, DOF, NQ, 4>); }
+  return go(quad_sf_kernel<DIM, P, DOF, NQ, 1>);
 }
 
 template <int DIM, int P, int DOF>

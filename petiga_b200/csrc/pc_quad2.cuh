@@ -101,8 +101,11 @@ struct SFCfg {
 };
 
 // NQ > 0: every used axis has exactly NQ quadrature points (the default rule NQ = p+1), loops unroll fully; NQ = 0: runtime
-template <int DIM, int P, int DOF, int NQ>
-__global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(const __grid_constant__ SFParams sp) {
+// MINB: resident CTAs per SM the register allocation is sized for.  MINB = 4 (<= 64 registers; the launcher picks it when
+// four of the element's shared-memory slots fit an SM) hides more of the ~10 barriers per element: 69.5 -> 64.5 ms at cfg 2;
+// with a larger slot (mapped geometry: 3 CTAs fit) the 77-register MINB = 1 build is the faster one.
+template <int DIM, int P, int DOF, int NQ, int MINB>
+__global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS, MINB) quad_sf_kernel(const __grid_constant__ SFParams sp) {
   using Cfg = SFCfg<DIM, P, DOF>;
   constexpr int n0 = Cfg::n0, n1 = Cfg::n1, n2 = Cfg::n2, NEN = Cfg::NEN, G = Cfg::G, NEN1 = P + 1;
   const KParams& prm = sp.k;
@@ -445,6 +448,12 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
   const int a0 = (lt / (n0 * n1)) % n0, a1 = lt / (n0 * n1 * n0), b0 = lt % n0, b1 = (lt / n0) % n1;
   const int ab0 = a0 * n0 + b0, ab1 = a1 * n1 + b1;
   const bool fix_mat = (prm.slot == PETIGA_SLOT_SYSTEM || prm.slot == PETIGA_SLOT_JACOBIAN || prm.slot == PETIGA_SLOT_IJACOBIAN);
+  bool elem_fix = false;   // does this element hold Dirichlet dofs? (boundary element on a face with values, petigaelem.c:1263-1283)
+  if (prm.any_bc)
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+      if (!prm.ax[d].periodic)
+        elem_fix = elem_fix || (ID[d] == 0 && prm.bc[d][0].vcount > 0) || (ID[d] == prm.ax[d].nel - 1 && prm.bc[d][1].vcount > 0);
   if (want_mat) {
     for (int ij = 0; ij < DOF * DOF; ij++) {
       if (!((ls.ijmask >> ij) & 1)) continue;     // uniform over the grid
@@ -513,28 +522,37 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
             }
           }
       }
-      // NURBS node weights, fix-up (petigaelem.c:1360-1389,1483-1501) and scatter of this block
+      // NURBS node weights, fix-up (petigaelem.c:1360-1389,1483-1501) and scatter of this block.  The closed-form position
+      // pos = Bk*W1*W0 + Sk*(Bj*W0 + Sj*Bi) + (Lk*Sj + Lj)*Si + Li is affine in the (a2,b2)-dependent bytes (Bk,Sk,Lk) with
+      // thread-constant coefficients, and only boundary elements can hold fixed dofs, so an entry costs one table load,
+      // three multiply-adds and the reduction (the address arithmetic was ~1/3 of the kernel's instructions before).
       if (valid) {
+        const uint32_t s0 = segs[a0 * NEN1 + b0], s1 = segs[NEN1 * NEN1 + a1 * NEN1 + b1];
+        const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
+        const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
+        const int W0 = Wd[a0], W1 = Wd[NEN1 + a1];
+        const int cB = W1 * W0, cS = Bj * W0 + Sj * Bi, cL = Sj * Si, c0 = Lj * Si + Li;
+        const bool fixing = fix_mat && elem_fix;
 #pragma unroll
         for (int x = 0; x < n2; x++) {
           const int a = a0 + n0 * (a1 + n1 * x);
           const int ra = a * DOF + bi;
           const int lr = lrow[a];
-          const int W0 = Wd[a0], W1 = Wd[NEN1 + a1], W2 = Wd[2 * NEN1 + x];
           int64_t base = prm.rowbase[lr];
           double* dst = prm.values;
           if (lr >= prm.nown) { dst = prm.ghost_values; base -= prm.nnz_own; }
-          const uint32_t s0 = segs[a0 * NEN1 + b0], s1 = segs[NEN1 * NEN1 + a1 * NEN1 + b1];
-          const int Bi = s0 & 255, Si = (s0 >> 8) & 255, Li = (s0 >> 16) & 255;
-          const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
+          if (DOF == 1) dst += base;
+          else if (prm.block) dst += (size_t)base * DOF * DOF + bj * DOF + bi;
+          else dst += (size_t)base * DOF * DOF + (size_t)bi * (cB * Wd[2 * NEN1 + x]) * DOF + bj;
+          const bool fr = fixing && fixflag[ra];
+          const double wa = rational ? We[a] : 1.0;
 #pragma unroll
           for (int y = 0; y < n2; y++) {
-            const int b = b0 + n0 * (b1 + n1 * y);
-            const int cb = b * DOF + bj;
             double v = acc[x][y];
-            if (rational) v *= We[a] * We[b];
-            if (fix_mat && prm.any_bc) {
-              const bool fr = fixflag[ra], fc = fixflag[cb];
+            if (rational) v *= wa * We[b0 + n0 * (b1 + n1 * y)];
+            if (fixing) {
+              const int cb = (b0 + n0 * (b1 + n1 * y)) * DOF + bj;
+              const bool fc = fixflag[cb];
               if (fr || fc) {
                 if (prm.slot == PETIGA_SLOT_SYSTEM && fc && !fr) atomicAdd(&Fe[ra], -v * FixVal[cb]);
                 v = (ra == cb) ? 1.0 : 0.0;
@@ -542,13 +560,10 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS) quad_sf_kernel(co
             }
             if (v == 0.0) continue;
             const uint32_t s2 = segs[2 * NEN1 * NEN1 + x * NEN1 + y];
-            const int Bk = s2 & 255, Sk = (s2 >> 8) & 255, Lk = (s2 >> 16) & 255;
-            const int pos = Bk * W1 * W0 + Sk * (Bj * W0 + Sj * Bi) + (Lk * Sj + Lj) * Si + Li;
-            size_t off;
-            if (DOF == 1) off = (size_t)(base + pos);
-            else if (prm.block) off = (size_t)(base + pos) * DOF * DOF + bj * DOF + bi;
-            else off = (size_t)base * DOF * DOF + (size_t)bi * (W0 * W1 * W2) * DOF + (size_t)pos * DOF + bj;
-            atomicAdd(dst + off, v);
+            const int pos = (int)(s2 & 255) * cB + (int)((s2 >> 8) & 255) * cS + (int)((s2 >> 16) & 255) * cL + c0;
+            double* p = (DOF == 1) ? dst + pos : (prm.block ? dst + (size_t)pos * DOF * DOF : dst + (size_t)pos * DOF);
+            if (!prm.noscatter) atomicAdd(p, v);
+            else if (v == 1.2345e300) *p = v;   // keeps the value and the address live
           }
         }
       }

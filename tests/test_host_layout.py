@@ -160,5 +160,6 @@ def test_hot_kernel_register_budget():
 
     if not os.path.exists(os.path.join(libdir, "pc_quad2.ptxas.log")):
         pytest.skip("library not built in-tree")
-    assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4") <= 85
+    assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4ELi1") <= 85
+    assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4ELi4") <= 64
     assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi1ELi3") <= 64
