@@ -62,7 +62,7 @@ __host__ __device__ constexpr int sf_n(int dim, int p, int d) { return d < dim ?
 
 // shared-memory carve-up of one element slot (offsets in doubles)
 struct SFSmem {
-  int b1d, pp0, pp1, p2, dp, fp, u1, ev, s1, s2, aq, cq, fq, fld, fe, r1, r2, geo, fixval, flux, ufix, ints, total;
+  int b1d, pp0, pp1, p2, dp, fp, u1, ev, s1, s2, aq, cq, fq, fld, fe, r1, r2, geo, fixval, flux, ufix, rbase, ints, total;
   __host__ __device__ SFSmem(int n0, int n1, int n2, int nq0, int nq1, int nq2, int dim, int dof, const SFLists& l, int NA, int NV, int per_qp, int NC) {
     const int nqp = nq0 * nq1 * nq2, nen = n0 * n1 * n2;
     int o = 0;
@@ -87,6 +87,7 @@ struct SFSmem {
     fixval = o; o += (nen * dof); o += (o & 1);
     flux = o; o += (nen * dof); o += (o & 1);
     ufix = o; o += (nen * dof); o += (o & 1);
+    rbase = o; o += nen;                                  // int64 value-array offset of every local node's row (prefetched in the header)
     ints = o; o += ((nen + nen * dof + 3 * 25 + 3 * 5 + 8) / 2 + 1); o += (o & 1);
     total = o + (o & 1);
   }
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS, MINB) quad_sf_ker
   double *Fld = sm + lay.fld, *Fe = sm + lay.fe, *Xq = sm + lay.r1, *JW = sm + lay.r1 + 3 * nqp, *We = sm + lay.r2;
   double *FixVal = sm + lay.fixval, *Flux = sm + lay.flux, *UFix = sm + lay.ufix, *Geo = sm + lay.geo;
   int* lrow = reinterpret_cast<int*>(sm + lay.ints);
+  int64_t* rbase = reinterpret_cast<int64_t*>(sm + lay.rbase);
   int* fixflag = lrow + NEN;
   uint32_t* segs = reinterpret_cast<uint32_t*>(fixflag + NEN * DOF);
   int* Wd = reinterpret_cast<int*>(segs + 3 * NEN1 * NEN1);
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS, MINB) quad_sf_ker
       const int gidx = g0 + prm.ax[0].gw * (g1 + prm.ax[1].gw * g2);
       const int lr = prm.localrow[gidx];
       lrow[a] = lr;
+      rbase[a] = want_mat ? prm.rowbase[lr] : 0;   // its L2 latency is paid here, under the header's other loads, not in the scatter
       const double wa = rational ? prm.Wt[gidx] : 1.0;
       We[a] = wa;
       if (mapped) {
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS, MINB) quad_sf_ker
           const int a = a0 + n0 * (a1 + n1 * x);
           const int ra = a * DOF + bi;
           const int lr = lrow[a];
-          int64_t base = prm.rowbase[lr];
+          int64_t base = rbase[a];
           double* dst = prm.values;
           if (lr >= prm.nown) { dst = prm.ghost_values; base -= prm.nnz_own; }
           if (DOF == 1) dst += base;
