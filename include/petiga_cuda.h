@@ -73,7 +73,8 @@ enum {
   PETIGA_FORM_BOUNDARYINTEGRAL = 8, /* demo/BoundaryIntegral.c:27-57 System: Laplace inside, F = N*1.0 on the faces
                                      enabled with petiga_cuda_set_boundary_form (p->atboundary branch)               */
   PETIGA_FORM_NEUMANN = 9,        /* demo/Neumann.c:28-45 SystemGalerkin: Laplace + f = 4 pi^2 sum_i sin(2 pi x_i)   */
-  PETIGA_NFORMS = 10
+  PETIGA_FORM_CAHNHILLIARD3D = 10, /* demo/CahnHilliard3D.c:54-169 Residual/Tangent; params = {theta, L0, lambda}          */
+  PETIGA_NFORMS = 11
 };
 
 /* built-in Scalar callbacks of petiga_cuda_compute_scalar (IGAComputeScalar, src/petigacomp.c:35-96) */

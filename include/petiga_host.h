@@ -85,6 +85,8 @@ PetscErrorCode IGADeviceForm_Elasticity3D_System(IGAPoint, PetscScalar *, PetscS
 PetscErrorCode IGADeviceForm_Elasticity_System(IGAPoint, PetscScalar *, PetscScalar *, void *);         /* ctx: {mu, lambda} as demo/Elasticity.c:10-13 */
 PetscErrorCode IGADeviceForm_CahnHilliard2D_Residual(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *); /* ctx: {theta, alpha} */
 PetscErrorCode IGADeviceForm_CahnHilliard2D_Tangent(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_CahnHilliard3D_Residual(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *); /* demo/CahnHilliard3D.c:54-107; ctx: {theta, L0, lambda} */
+PetscErrorCode IGADeviceForm_CahnHilliard3D_Tangent(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_Function(IGAPoint, const PetscScalar *, PetscScalar *, void *);      /* ctx: {lambda}                       */
 PetscErrorCode IGADeviceForm_Bratu_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_IFunction(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);

@@ -75,7 +75,7 @@ typedef struct {
 
 enum { SLOT_VECTOR=0, SLOT_MATRIX, SLOT_SYSTEM, SLOT_FUNCTION, SLOT_JACOBIAN, SLOT_IFUNCTION, SLOT_IJACOBIAN };
 enum { FORM_POISSON=0, FORM_LAPLACE, FORM_L2PROJECTION, FORM_ELASTICITY3D, FORM_ELASTICITY,
-       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN };
+       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN, FORM_CAHNHILLIARD3D };
 
 /* ------------------------------------------------------------------------------------------ */
 /* axis: src/petigaaxis.c                                                                     */
@@ -1088,6 +1088,28 @@ static int form_function(int form, const double *prm, const Point *p, double shi
       R[a] = Ra;
     }
     return 0; }
+  case FORM_CAHNHILLIARD3D: { /* demo/CahnHilliard3D.c:54-107 (Residual), :11-52 */
+    double theta = prm[0], L0 = prm[1], lambda = prm[2];
+    double c_t, c, M, dM, dmu, c1[3], c2[9], c_x, c_y, c_z, c_xx, c_yy, c_zz, t1; int cc;
+    get_value(p,V,&c_t); get_value(p,U,&c);
+    M = c*(1-c); dM = 1-2*c;
+    dmu = 0.5/theta*1.0/(c*(1-c)) - 2; dmu *= L0*L0/lambda;
+    get_grad(p,U,c1);
+    for (cc = 0; cc < 9; cc++) c2[cc] = 0;                     /* IGAPointFormHess -> IGA_GetHess (petigaval.F90:216-232) */
+    for (a = 0; a < nen; a++) for (cc = 0; cc < 9; cc++) c2[cc] = c2[cc] + p->N2[a*9+cc]*U[a];
+    c_x = c1[0]; c_y = c1[1]; c_z = c1[2]; c_xx = c2[0]; c_yy = c2[4]; c_zz = c2[8];
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*3], Na_y = p->N1[a*3+1], Na_z = p->N1[a*3+2];
+      double Na_xx = p->N2[a*9+0], Na_yy = p->N2[a*9+4], Na_zz = p->N2[a*9+8], Ra = 0;
+      Ra += Na * c_t;
+      t1 = M*dmu + dM*(c_xx+c_yy+c_zz);
+      Ra += Na_x * t1 * c_x;
+      Ra += Na_y * t1 * c_y;
+      Ra += Na_z * t1 * c_z;
+      Ra += (Na_xx+Na_yy+Na_zz) * M * (c_xx+c_yy+c_zz);
+      R[a] = Ra;
+    }
+    return 0; }
   case FORM_BRATU: { /* demo/BratuFJ.F90: Function (:22-62), IFunction (:118-150) */
     double lambda = prm[0], u, v = 0, gu[3];
     get_value(p,U,&u); get_grad(p,U,gu);
@@ -1132,6 +1154,38 @@ static int form_jacobian(int form, const double *prm, const Point *p, double shi
         t3 = t2*Nb + dM*del2_Nb;
         Kab += (Na_x * c_x + Na_y * c_y) * t3;
         Kab += del2_Na * (dM*del2_c*Nb + M*del2_Nb);
+        K[a*nen+b] = Kab;
+      }
+    }
+    return 0; }
+  case FORM_CAHNHILLIARD3D: { /* demo/CahnHilliard3D.c:109-169 (Tangent) */
+    double theta = prm[0], L0 = prm[1], lambda = prm[2];
+    double c, M, dM, d2M, dmu, d2mu, c1[3], c2[9], c_x, c_y, c_z, c_xx, c_yy, c_zz; int cc;
+    get_value(p,U,&c);
+    M = c*(1-c); dM = 1-2*c; d2M = -2;
+    dmu = 0.5/theta*1.0/(c*(1-c)) - 2; dmu *= L0*L0/lambda;
+    d2mu = -0.5/theta*(1-2*c)/(c*c*(1-c)*(1-c)); d2mu *= L0*L0/lambda;
+    get_grad(p,U,c1);
+    for (cc = 0; cc < 9; cc++) c2[cc] = 0;
+    for (a = 0; a < nen; a++) for (cc = 0; cc < 9; cc++) c2[cc] = c2[cc] + p->N2[a*9+cc]*U[a];
+    c_x = c1[0]; c_y = c1[1]; c_z = c1[2]; c_xx = c2[0]; c_yy = c2[4]; c_zz = c2[8];
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*3], Na_y = p->N1[a*3+1], Na_z = p->N1[a*3+2];
+      double Na_xx = p->N2[a*9+0], Na_yy = p->N2[a*9+4], Na_zz = p->N2[a*9+8];
+      for (b = 0; b < nen; b++) {
+        double Nb = p->N0[b], Nb_x = p->N1[b*3], Nb_y = p->N1[b*3+1], Nb_z = p->N1[b*3+2];
+        double Nb_xx = p->N2[b*9+0], Nb_yy = p->N2[b*9+4], Nb_zz = p->N2[b*9+8];
+        double Kab = 0, t1, t2;
+        Kab += shift*Na*Nb;
+        t1 = M*dmu + dM*(c_xx+c_yy+c_zz);
+        Kab += Na_x * t1 * Nb_x;
+        Kab += Na_y * t1 * Nb_y;
+        Kab += Na_z * t1 * Nb_z;
+        t2 = (dM*dmu+M*d2mu+d2M*(c_xx+c_yy+c_zz))*Nb + dM*(Nb_xx+Nb_yy+Nb_zz);
+        Kab += Na_x * t2 * c_x;
+        Kab += Na_y * t2 * c_y;
+        Kab += Na_z * t2 * c_z;
+        Kab += (Na_xx+Na_yy+Na_zz) * (dM*(c_xx+c_yy+c_zz)*Nb + M*(Nb_xx+Nb_yy+Nb_zz));
         K[a*nen+b] = Kab;
       }
     }

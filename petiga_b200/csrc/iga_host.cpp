@@ -269,6 +269,8 @@ const FormEntry* lookup_form(const void* fn, int slot) {
       {FN(IGADeviceForm_Elasticity_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_ELASTICITY, 2, 1},
       {FN(IGADeviceForm_CahnHilliard2D_Residual), PETIGA_SLOT_IFUNCTION, PETIGA_FORM_CAHNHILLIARD2D, 2, 0},
       {FN(IGADeviceForm_CahnHilliard2D_Tangent), PETIGA_SLOT_IJACOBIAN, PETIGA_FORM_CAHNHILLIARD2D, 2, 0},
+      {FN(IGADeviceForm_CahnHilliard3D_Residual), PETIGA_SLOT_IFUNCTION, PETIGA_FORM_CAHNHILLIARD3D, 3, 0},
+      {FN(IGADeviceForm_CahnHilliard3D_Tangent), PETIGA_SLOT_IJACOBIAN, PETIGA_FORM_CAHNHILLIARD3D, 3, 0},
       {FN(IGADeviceForm_Bratu_Function), PETIGA_SLOT_FUNCTION, PETIGA_FORM_BRATU, 1, 0},
       {FN(IGADeviceForm_Bratu_Jacobian), PETIGA_SLOT_JACOBIAN, PETIGA_FORM_BRATU, 1, 0},
       {FN(IGADeviceForm_Bratu_IFunction), PETIGA_SLOT_IFUNCTION, PETIGA_FORM_BRATU, 1, 0},
@@ -311,6 +313,7 @@ SENT4(IGADeviceForm_BoundaryIntegral_System) SENT4(IGADeviceForm_Neumann_SystemG
 PetscErrorCode IGADeviceExact_Neumann(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 SENT4(IGADeviceForm_Elasticity3D_System) SENT4(IGADeviceForm_Elasticity_System)
 SENTI(IGADeviceForm_CahnHilliard2D_Residual) SENTI(IGADeviceForm_CahnHilliard2D_Tangent)
+SENTI(IGADeviceForm_CahnHilliard3D_Residual) SENTI(IGADeviceForm_CahnHilliard3D_Tangent)
 PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar*, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 PetscErrorCode IGADeviceExact_ErrNormTest(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 PetscErrorCode IGADeviceExact_L2Projection(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }

@@ -78,6 +78,11 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       if (slot == PETIGA_SLOT_IFUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 4; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
       if (slot == PETIGA_SLOT_IJACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 4; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
       break;
+    case PETIGA_FORM_CAHNHILLIARD3D:
+      if (dim != 3 || dof != 1) break;
+      if (slot == PETIGA_SLOT_IFUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 5; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
+      if (slot == PETIGA_SLOT_IJACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 5; f.per_qp = 1; f.needs_state = 1; f.order = 2; }
+      break;
     case PETIGA_FORM_BRATU:
       if (dof != 1) break;
       if (fun) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
@@ -183,21 +188,30 @@ __host__ __device__ inline void form_coefficients(int form, int slot, const doub
       break;
     }
 #undef CE
-    case PETIGA_FORM_CAHNHILLIARD2D: {  // demo/CahnHilliard2D.c:9-32,84-197
-      const double theta = prm[0], alpha = prm[1];
-      const double c = q.u[0], c_t = q.v[0], c_x = q.gu[0][0], c_y = q.gu[0][1], del2_c = q.d2u[0];
+    case PETIGA_FORM_CAHNHILLIARD2D:    // demo/CahnHilliard2D.c:9-32,84-197  (chemical potential scaled by 3*alpha)
+    case PETIGA_FORM_CAHNHILLIARD3D: {  // demo/CahnHilliard3D.c:11-52,54-169 (scaled by L0^2/lambda); same residual/tangent in DIM dims
+      const double theta = prm[0];
+      const double scale = (form == PETIGA_FORM_CAHNHILLIARD2D) ? 3 * prm[1] : prm[1] * prm[1] / prm[2];
+      const double c = q.u[0], c_t = q.v[0], del2_c = q.d2u[0];
       const double M = c * (1 - c), dM = 1 - 2 * c, d2M = -2;
-      double dmu = 0.5 / theta * 1 / (c * (1 - c)) - 2; dmu *= 3 * alpha;
+      double dmu = 0.5 / theta * 1 / (c * (1 - c)) - 2; dmu *= scale;
       const double t1 = M * dmu + dM * del2_c;
-      if (fv && NV) { fv[0] = c_t; fv[1] = c_x * t1; fv[2] = c_y * t1; fv[3] = M * del2_c; }
+      if (fv && NV) {
+        fv[0] = c_t;
+        for (int d = 0; d < DIM; d++) fv[1 + d] = q.gu[0][d] * t1;
+        fv[1 + DIM] = M * del2_c;
+      }
       if (C && NA) {
-        double d2mu = 0.5 / theta * (2 * c - 1) / (c * c * (1 - c) * (1 - c)); d2mu *= 3 * alpha;
+        double d2mu = 0.5 / theta * (2 * c - 1) / (c * c * (1 - c) * (1 - c)); d2mu *= scale;
         const double t2 = (dM * dmu + M * d2mu + d2M * del2_c);
         C[0 * NA + 0] = shift;
-        C[1 * NA + 1] = t1; C[2 * NA + 2] = t1;
-        C[1 * NA + 0] = c_x * t2; C[1 * NA + 3] = c_x * dM;
-        C[2 * NA + 0] = c_y * t2; C[2 * NA + 3] = c_y * dM;
-        C[3 * NA + 0] = dM * del2_c; C[3 * NA + 3] = M;
+        for (int d = 0; d < DIM; d++) {
+          C[(1 + d) * NA + (1 + d)] = t1;
+          C[(1 + d) * NA + 0] = q.gu[0][d] * t2;
+          C[(1 + d) * NA + (1 + DIM)] = q.gu[0][d] * dM;
+        }
+        C[(1 + DIM) * NA + 0] = dM * del2_c;
+        C[(1 + DIM) * NA + (1 + DIM)] = M;
       }
       break;
     }

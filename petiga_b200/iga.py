@@ -23,6 +23,7 @@ FORMS = {
     "ELASTICITY3D": {"SYSTEM": "IGADeviceForm_Elasticity3D_System"},
     "ELASTICITY": {"SYSTEM": "IGADeviceForm_Elasticity_System"},
     "CAHNHILLIARD2D": {"IFUNCTION": "IGADeviceForm_CahnHilliard2D_Residual", "IJACOBIAN": "IGADeviceForm_CahnHilliard2D_Tangent"},
+    "CAHNHILLIARD3D": {"IFUNCTION": "IGADeviceForm_CahnHilliard3D_Residual", "IJACOBIAN": "IGADeviceForm_CahnHilliard3D_Tangent"},
     "BRATU": {"FUNCTION": "IGADeviceForm_Bratu_Function", "JACOBIAN": "IGADeviceForm_Bratu_Jacobian",
               "IFUNCTION": "IGADeviceForm_Bratu_IFunction", "IJACOBIAN": "IGADeviceForm_Bratu_IJacobian"},
 }

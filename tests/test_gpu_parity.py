@@ -187,6 +187,19 @@ def test_nurbs_quarter_annulus(form, params):
         assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6
 
 
+# ---- CahnHilliard3D (demo/CahnHilliard3D.c): order-2 form with state in 3-D, periodic, both quadrature kernels ----------
+@pytest.mark.parametrize("p,N", [(2, 6), (3, 8)])
+def test_cahnhilliard3d(p, N):
+    case = Case(3, p=p, N=N, C=p - 1, periodic=True, order=2)
+    o = case.oracle(); o.setup()
+    n = len(o.pattern()[0]) - 1
+    U, V = state_vectors(n)
+    prm = [1.5, 1.0, 0.75 / N ** 2]
+    for impl in ((0, 1) if p == 2 else (None,)):     # p = 3: 49 tensor pairs do not fit the sum-factorised kernel's slot; auto falls to the pair loop
+        check_against_oracle(case, "IFUNCTION", "CAHNHILLIARD3D", prm, U=U, V=V, shift=1e3, tol=TOL, quad_impl=impl)
+        check_against_oracle(case, "IJACOBIAN", "CAHNHILLIARD3D", prm, U=U, V=V, shift=1e3, tol=TOL, quad_impl=impl)
+
+
 # ---- large elements: 3-D p=3 dof=3 and p=4 dof 2-3 (only the sum-factorised kernel instantiates them) -----------------
 @pytest.mark.parametrize("p,dof,form,prm", [(3, 3, "ELASTICITY3D", [1.0, 1.0]), (4, 2, "MASS", []), (4, 3, "ELASTICITY", [2.0, 0.5])])
 def test_large_element_block_forms(p, dof, form, prm):

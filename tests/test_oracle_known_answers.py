@@ -329,10 +329,11 @@ def make_mass_rhs(N):
     ("BRATU", "FUNCTION", "JACOBIAN", 2, False, [6.8]),
     ("BRATU", "IFUNCTION", "IJACOBIAN", 2, False, [6.8]),
     ("CAHNHILLIARD2D", "IFUNCTION", "IJACOBIAN", 2, True, [1.5, 3000.0]),
+    ("CAHNHILLIARD3D", "IFUNCTION", "IJACOBIAN", 3, True, [1.5, 1.0, 0.003]),     # demo/CahnHilliard3D.c: theta, L0, lambda = tau*h^2
     ("POISSON", "FUNCTION", "JACOBIAN", 3, False, []),
 ])
 def test_jacobian_matches_finite_difference(form, slotf, slotj, dim, periodic, params):
-    o = make(dim, p=2, N=5 if dim == 2 else 3, periodic=periodic)
+    o = make(dim, p=2, N=5 if dim == 2 else (4 if periodic else 3), periodic=periodic)
     if not periodic:
         for d in range(dim):
             o.boundary_value(d, 0, 0, 0.25)
