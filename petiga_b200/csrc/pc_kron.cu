@@ -145,7 +145,7 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 // row in storage order, so every store instruction writes 256 contiguous bytes.
 // PF > 0: all axes have degree PF, so a full-width interior row has compile-time extents and its loop unrolls completely
 template <int DOF, int PF>
-__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 1) kron_rows_kernel(const __grid_constant__ KronParams kp) {
+__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(const __grid_constant__ KronParams kp) {
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
