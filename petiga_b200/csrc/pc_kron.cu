@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
     const int Ai_ = ls0 + il_, gi_ = Ai_ - gs0;
     r.Wi = __ldg(Wg0 + gi_); r.fi = __ldg(first0 + Ai_); r.simple = __ldg(simple0 + gi_);
     r.base = __ldg(rowbase + il_ + lr0);
-    r.a0 = __ldg(M0 + (size_t)Ai_ * kMaxW + ciF); r.a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai_) * kMaxW + ciF);
+    r.a0 = r.a3 = 0.0;
+    if (DOF == 1) { r.a0 = __ldg(M0 + (size_t)Ai_ * kMaxW + ciF); r.a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai_) * kMaxW + ciF); }   // only the scalar fast paths use them
     return r;
   };
   RowP cur = {0, 0, 0, 0, 0.0, 0.0}, nxt = cur;
