@@ -74,7 +74,8 @@ enum {
                                      enabled with petiga_cuda_set_boundary_form (p->atboundary branch)               */
   PETIGA_FORM_NEUMANN = 9,        /* demo/Neumann.c:28-45 SystemGalerkin: Laplace + f = 4 pi^2 sum_i sin(2 pi x_i)   */
   PETIGA_FORM_CAHNHILLIARD3D = 10, /* demo/CahnHilliard3D.c:54-169 Residual/Tangent; params = {theta, L0, lambda}          */
-  PETIGA_NFORMS = 11
+  PETIGA_FORM_CONVTEST = 11,      /* test/ConvTest.c:30-69 Galerkin (reaction-diffusion); params = {c, k}                */
+  PETIGA_NFORMS = 12
 };
 
 /* built-in Scalar callbacks of petiga_cuda_compute_scalar (IGAComputeScalar, src/petigacomp.c:35-96) */
@@ -82,7 +83,7 @@ enum {
   PETIGA_SCALAR_ERRNORM = 0,      /* ErrorSqr of IGAComputeErrorNorm (src/petigacomp.c:103-124): n = dof squared errors;
                                      params = {k (0..2), exact id, choice}; exact id 0 = NULL, 1 = test/IGAErrNorm.c:26-52
                                      (dof 4), 2 = demo/L2Projection.c:3-61 function `choice` (k = 0), 3 = demo/Neumann.c:5-8
-                                     Solution (k = 0)                                                                      */
+                                     Solution (k = 0), 4 = test/ConvTest.c:8-28 prod sin(pi x_i) (k = 0, 1)                */
   PETIGA_SCALAR_CH_STATS = 1,     /* demo/CahnHilliard2D.c:36-58 monitor: n = 3 (free energy, 2nd, 3rd moment);
                                      params = {theta, alpha, cbar}                                                          */
   PETIGA_NSCALARS = 2

@@ -81,6 +81,7 @@ PetscErrorCode IGADeviceForm_Mass_Matrix(IGAPoint, PetscScalar *, void *);      
 PetscErrorCode IGADeviceForm_Mass_Vector(IGAPoint, PetscScalar *, void *);                              /* test/IGACreate.c Vector             */
 PetscErrorCode IGADeviceForm_BoundaryIntegral_System(IGAPoint, PetscScalar *, PetscScalar *, void *);   /* demo/BoundaryIntegral.c:50-57 System (Laplace + face term) */
 PetscErrorCode IGADeviceForm_Neumann_SystemGalerkin(IGAPoint, PetscScalar *, PetscScalar *, void *);    /* demo/Neumann.c:28-45                                       */
+PetscErrorCode IGADeviceForm_ConvTest_Galerkin(IGAPoint, PetscScalar *, PetscScalar *, void *);         /* test/ConvTest.c:51-69; ctx: {c, k}                         */
 PetscErrorCode IGADeviceForm_Elasticity3D_System(IGAPoint, PetscScalar *, PetscScalar *, void *);       /* ctx: {lambda, mu}                   */
 PetscErrorCode IGADeviceForm_Elasticity_System(IGAPoint, PetscScalar *, PetscScalar *, void *);         /* ctx: {mu, lambda} as demo/Elasticity.c:10-13 */
 PetscErrorCode IGADeviceForm_CahnHilliard2D_Residual(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *); /* ctx: {theta, alpha} */
@@ -95,6 +96,7 @@ PetscErrorCode IGADeviceForm_Bratu_IJacobian(IGAPoint, PetscReal, const PetscSca
 /* Scalar / Exact sentinels for IGAComputeScalar and IGAComputeErrorNorm (src/petigacomp.c:35-186) */
 PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar *, PetscInt, PetscScalar *, void *);  /* demo/CahnHilliard2D.c:43-58; ctx: {theta, alpha, cbar} */
 PetscErrorCode IGADeviceExact_ErrNormTest(IGAPoint, PetscInt, PetscScalar *, void *);     /* test/IGAErrNorm.c:26-52 (dof 4: 1, sum x, sum x^2, prod x) */
+PetscErrorCode IGADeviceExact_ConvTest(IGAPoint, PetscInt, PetscScalar *, void *);        /* test/ConvTest.c:104-111 (k = 0, 1)                            */
 PetscErrorCode IGADeviceExact_Neumann(IGAPoint, PetscInt, PetscScalar *, void *);         /* demo/Neumann.c:80-86 (k = 0)                                  */
 PetscErrorCode IGADeviceExact_L2Projection(IGAPoint, PetscInt, PetscScalar *, void *);    /* demo/L2Projection.c:3-61; ctx: {PetscReal choice}; k = 0     */
 

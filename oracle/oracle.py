@@ -14,7 +14,7 @@ _LIB = None
 
 SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6)
 FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7,
-            BOUNDARYINTEGRAL=8, NEUMANN=9, CAHNHILLIARD3D=10)
+            BOUNDARYINTEGRAL=8, NEUMANN=9, CAHNHILLIARD3D=10, CONVTEST=11)
 SCALAR = dict(ERRNORM=0, CH_STATS=1)
 
 _dp = C.POINTER(C.c_double)

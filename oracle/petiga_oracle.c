@@ -75,7 +75,7 @@ typedef struct {
 
 enum { SLOT_VECTOR=0, SLOT_MATRIX, SLOT_SYSTEM, SLOT_FUNCTION, SLOT_JACOBIAN, SLOT_IFUNCTION, SLOT_IJACOBIAN };
 enum { FORM_POISSON=0, FORM_LAPLACE, FORM_L2PROJECTION, FORM_ELASTICITY3D, FORM_ELASTICITY,
-       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN, FORM_CAHNHILLIARD3D };
+       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN, FORM_CAHNHILLIARD3D, FORM_CONVTEST };
 
 /* ------------------------------------------------------------------------------------------ */
 /* axis: src/petigaaxis.c                                                                     */
@@ -1051,6 +1051,12 @@ static int form_system(int form, const double *prm, const Point *p, double *K, d
     f = 4*M_PI*M_PI * (sin(2*M_PI*xx[0]) + sin(2*M_PI*xx[1]) + sin(2*M_PI*xx[2]));
     for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i]; K[a*nen+b] = sum; } F[a] = p->N0[a]*f; }
     return 0; }
+  case FORM_CONVTEST: { /* test/ConvTest.c:30-69 Galerkin: c N_a N_b + k grad N_a . grad N_b, f = (c + k dim pi^2) prod sin(pi x_i) */
+    double c = prm[0], k = prm[1], f = c + k*dim*M_PI*M_PI;
+    for (i = 0; i < dim; i++) f *= sin(M_PI*p->x[i]);
+    for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i];
+      K[a*nen+b] = c*p->N0[a]*p->N0[b] + k*sum; } F[a] = p->N0[a]*f; }
+    return 0; }
   case FORM_ELASTICITY: { /* demo/Elasticity.c:22-52; dof == dim */
     double lambda = prm[0], mu = prm[1];
     for (a = 0; a < nen; a++) for (b = 0; b < nen; b++) {
@@ -1479,6 +1485,13 @@ static int exact_eval(int id, int choice, int dim, int dof, const double *x, int
   }
   if (id == 2) { double xx[3] = {0,0,0}; if (k != 0) return 1; for (i = 0; i < dim; i++) xx[i] = x[i];
     for (c = 0; c < dof; c++) value[c] = l2_function(choice, dim, xx); return 0; }
+  if (id == 4) { /* test/ConvTest.c:8-28,104-111: prod sin(pi x_i), value (k = 0) or gradient (k = 1) */
+    if (k > 1) return 1;
+    for (c = 0; c < dof; c++) {
+      if (k == 0) { double v = 1; for (i = 0; i < dim; i++) v *= sin(M_PI*x[i]); value[c] = v; }
+      else for (i = 0; i < dim; i++) { double g = 1; for (j = 0; j < dim; j++) g *= (i == j) ? M_PI*cos(M_PI*x[j]) : sin(M_PI*x[j]); value[c*dim+i] = g; }
+    }
+    return 0; }
   if (id == 3) { double xx[3] = {0,0,0}; if (k != 0) return 1; for (i = 0; i < dim; i++) xx[i] = x[i];   /* demo/Neumann.c:5-8,80-86 Solution */
     for (c = 0; c < dof; c++) value[c] = sin(2*M_PI*xx[0]) + sin(2*M_PI*xx[1]) + sin(2*M_PI*xx[2]); return 0; }
   return 1;

@@ -263,6 +263,7 @@ const FormEntry* lookup_form(const void* fn, int slot) {
       {FN(IGADeviceForm_Mass_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_MASS, 0, 0},
       {FN(IGADeviceForm_BoundaryIntegral_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_BOUNDARYINTEGRAL, 0, 0},
       {FN(IGADeviceForm_Neumann_SystemGalerkin), PETIGA_SLOT_SYSTEM, PETIGA_FORM_NEUMANN, 0, 0},
+      {FN(IGADeviceForm_ConvTest_Galerkin), PETIGA_SLOT_SYSTEM, PETIGA_FORM_CONVTEST, 2, 0},
       {FN(IGADeviceForm_Mass_Matrix), PETIGA_SLOT_MATRIX, PETIGA_FORM_MASS, 0, 0},
       {FN(IGADeviceForm_Mass_Vector), PETIGA_SLOT_VECTOR, PETIGA_FORM_MASS, 0, 0},
       {FN(IGADeviceForm_Elasticity3D_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_ELASTICITY3D, 2, 0},
@@ -309,7 +310,8 @@ const char* IGAGetLastErrorMessage(void) { return g_msg.c_str(); }
 SENT4(IGADeviceForm_Poisson_System) SENTF(IGADeviceForm_Poisson_Function) SENTF(IGADeviceForm_Poisson_Jacobian)
 SENT4(IGADeviceForm_Laplace_System) SENT4(IGADeviceForm_L2Projection_System) SENT4(IGADeviceForm_Mass_System)
 SENT3(IGADeviceForm_Mass_Matrix) SENT3(IGADeviceForm_Mass_Vector)
-SENT4(IGADeviceForm_BoundaryIntegral_System) SENT4(IGADeviceForm_Neumann_SystemGalerkin)
+SENT4(IGADeviceForm_BoundaryIntegral_System) SENT4(IGADeviceForm_Neumann_SystemGalerkin) SENT4(IGADeviceForm_ConvTest_Galerkin)
+PetscErrorCode IGADeviceExact_ConvTest(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 PetscErrorCode IGADeviceExact_Neumann(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 SENT4(IGADeviceForm_Elasticity3D_System) SENT4(IGADeviceForm_Elasticity_System)
 SENTI(IGADeviceForm_CahnHilliard2D_Residual) SENTI(IGADeviceForm_CahnHilliard2D_Tangent)
@@ -721,6 +723,7 @@ PetscErrorCode IGAComputeErrorNorm(IGA g, PetscInt k, Vec vecU, IGAFormExact Exa
   double prm[3] = {(double)k, 0.0, 0.0};
   if (Exact == IGADeviceExact_ErrNormTest) prm[1] = 1;
   else if (Exact == IGADeviceExact_Neumann) prm[1] = 3;
+  else if (Exact == IGADeviceExact_ConvTest) prm[1] = 4;
   else if (Exact == IGADeviceExact_L2Projection) { prm[1] = 2; if (!ctx) return fail(PETSC_ERR_ARG_NULL, "IGADeviceExact_L2Projection needs {choice}"); prm[2] = *(const double*)ctx; }
   else if (Exact) return fail(PETSC_ERR_SUP, "IGAComputeErrorNorm: host callbacks cannot run on the GPU; pass one of the IGADeviceExact_* sentinels or NULL");
   if (PetscErrorCode e = ensure_plan(g)) return e;

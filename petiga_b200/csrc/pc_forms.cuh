@@ -61,6 +61,10 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       if (dof != 1 || slot != PETIGA_SLOT_SYSTEM) break;
       f.valid = 1; f.mc0 = 1; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 1; f.per_qp = 1; f.needs_x = 1; f.order = 1;
       break;
+    case PETIGA_FORM_CONVTEST:
+      if (dof != 1 || slot != PETIGA_SLOT_SYSTEM) break;
+      f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 1; f.per_qp = 1; f.needs_x = 1; f.order = 1;
+      break;
     case PETIGA_FORM_MASS:
       if (!lin || dof > kMaxDof) break;
       f.valid = 1; f.mc0 = 0; f.mc1 = 1; f.vc0 = 0; f.vc1 = 1; f.order = 0; f.constant_f = 1;
@@ -89,7 +93,7 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       if (jac) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
       break;
   }
-  f.mat_const = !f.per_qp || form == PETIGA_FORM_L2PROJECTION || form == PETIGA_FORM_NEUMANN;
+  f.mat_const = !f.per_qp || form == PETIGA_FORM_L2PROJECTION || form == PETIGA_FORM_NEUMANN || form == PETIGA_FORM_CONVTEST;
   if (slot == PETIGA_SLOT_VECTOR) { f.mc0 = f.mc1 = 0; }
   if (slot == PETIGA_SLOT_MATRIX) { f.vc0 = f.vc1 = 0; }
   return f;
@@ -152,6 +156,12 @@ __host__ __device__ inline void form_coefficients(int form, int slot, const doub
     case PETIGA_FORM_NEUMANN: {   // demo/Neumann.c:10-13,28-45
       if (C && NA) for (int d = 0; d < DIM; d++) C[d * NA + d] = 1.0;
       if (fv && NV) fv[0] = 4 * M_PI * M_PI * (sin(2 * M_PI * q.x[0]) + sin(2 * M_PI * q.x[1]) + sin(2 * M_PI * q.x[2]));
+      break;
+    }
+    case PETIGA_FORM_CONVTEST: {   // test/ConvTest.c:30-69: c N_a N_b + k grad N_a . grad N_b ; f = (c + k dim pi^2) prod sin(pi x_i)
+      const double c = prm[0], k = prm[1];
+      if (C && NA) { C[0] = c; for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = k; }
+      if (fv && NV) { double f = c + k * DIM * M_PI * M_PI; for (int d = 0; d < DIM; d++) f *= sin(M_PI * q.x[d]); fv[0] = f; }
       break;
     }
     case PETIGA_FORM_L2PROJECTION:  // demo/L2Projection.c:81-85

@@ -69,6 +69,14 @@ __device__ void exact_field(int id, int choice, int i, const double* x, int k, d
     double xx[3] = {0, 0, 0};
     for (int d = 0; d < DIM; d++) xx[d] = x[d];
     out[0] = l2_function(choice, DIM, xx);
+  } else if (id == 4 && k <= 1) {   // test/ConvTest.c:8-28 Solution: prod sin(pi x_i) and its gradient
+    if (k == 0) { double v = 1.0; for (int d = 0; d < DIM; d++) v *= sin(M_PI * x[d]); out[0] = v; }
+    else
+      for (int a = 0; a < DIM; a++) {
+        double g = 1.0;
+        for (int b = 0; b < DIM; b++) g *= (a == b) ? M_PI * cos(M_PI * x[b]) : sin(M_PI * x[b]);
+        out[a] = g;
+      }
   } else if (id == 3 && k == 0) {   // demo/Neumann.c:5-8 Solution (x has zeros above DIM)
     double xx[3] = {0, 0, 0};
     for (int d = 0; d < DIM; d++) xx[d] = x[d];
@@ -310,7 +318,7 @@ extern "C" int petiga_cuda_compute_scalar(petiga_cuda_plan* P, int scalar_id, co
     if (k < 0) { set_error("IGAComputeErrorNorm: derivative index must be nonnegative"); return PETIGA_CUDA_ERR_ARG; }   // petigacomp.c:170
     if (k > 2) { set_error("compute_scalar: error norms above the H2 seminorm are not available on the device path"); return PETIGA_CUDA_ERR_SUP; }
     if (n != L.dof || L.dof > kMaxDof) { set_error("compute_scalar: ERRNORM produces dof (<= 4) scalars"); return PETIGA_CUDA_ERR_ARG; }
-    if (ex < 0 || ex > 3 || (ex == 1 && L.dof != 4) || (ex >= 2 && k != 0)) { set_error("compute_scalar: exact solution id not applicable"); return PETIGA_CUDA_ERR_SUP; }
+    if (ex < 0 || ex > 4 || (ex == 1 && L.dof != 4) || ((ex == 2 || ex == 3) && k != 0) || (ex == 4 && k > 1)) { set_error("compute_scalar: exact solution id not applicable"); return PETIGA_CUDA_ERR_SUP; }
     kmax = k;
   } else if (scalar_id == PETIGA_SCALAR_CH_STATS) {
     if (L.dim != 2 || L.dof != 1 || n != 3 || !U) { set_error("compute_scalar: CH_STATS needs dim 2, dof 1, n 3 and a state vector"); return PETIGA_CUDA_ERR_ARG; }

@@ -19,6 +19,7 @@ FORMS = {
     "L2PROJECTION": {"SYSTEM": "IGADeviceForm_L2Projection_System"},
     "BOUNDARYINTEGRAL": {"SYSTEM": "IGADeviceForm_BoundaryIntegral_System"},
     "NEUMANN": {"SYSTEM": "IGADeviceForm_Neumann_SystemGalerkin"},
+    "CONVTEST": {"SYSTEM": "IGADeviceForm_ConvTest_Galerkin"},
     "MASS": {"SYSTEM": "IGADeviceForm_Mass_System", "MATRIX": "IGADeviceForm_Mass_Matrix", "VECTOR": "IGADeviceForm_Mass_Vector"},
     "ELASTICITY3D": {"SYSTEM": "IGADeviceForm_Elasticity3D_System"},
     "ELASTICITY": {"SYSTEM": "IGADeviceForm_Elasticity_System"},

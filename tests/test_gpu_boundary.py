@@ -88,3 +88,20 @@ def test_neumann_demo_error_norm_on_device():
     vU = g.CreateVec(); vU.set(U)
     got = g.ComputeErrorNorm(0, vU, "Neumann") ** 2
     assert abs(got[0] - exp[0]) <= 1e-12 * abs(exp[0])
+
+
+@pytest.mark.parametrize("dim,p,N", [(1, 3, 12), (2, 2, 9), (3, 3, 4), (3, 1, 6)])
+def test_convtest_system_and_error_norms(dim, p, N):
+    """test/ConvTest.c: reaction-diffusion system and the L2 / H1 error functionals of its exact solution."""
+    case = Case(dim, p=p, N=N, order=1, bcv=[(d, s, 0, 0.0) for d in range(dim) for s in range(2)])
+    check_against_oracle(case, "SYSTEM", "CONVTEST", [1.5, 0.5], tol=TOL)
+    o = case.oracle()
+    inf = o.setup()
+    n = int(np.prod(inf["nnp"][:dim]))
+    U = np.random.default_rng(8).standard_normal(n)
+    g = case.product()
+    vU = g.CreateVec(); vU.set(U)
+    for k in (0, 1):
+        exp = o.compute_scalar("ERRNORM", [k, 4, 0], 1, U=U)
+        got = g.ComputeErrorNorm(k, vU, "ConvTest") ** 2
+        assert abs(got[0] - exp[0]) <= 1e-12 * abs(exp[0]), (k, got, exp)

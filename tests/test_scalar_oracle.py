@@ -107,3 +107,37 @@ def test_cahnhilliard_stats_of_constant_state():
     assert abs(got[0] - e) < 1e-13 and abs(got[1]) < 1e-28 and abs(got[2]) < 1e-40
     got4 = o.compute_scalar("CH_STATS", [theta, alpha, c], 3, U=np.full(n, c), size=4)
     assert np.allclose(got4, got, rtol=1e-13, atol=1e-30)
+
+
+# test/ConvTest.c + test/ConvTest.py: reaction-diffusion with u = prod sin(pi x_i); rates p+1 (L2) and p (H1), tolerance 0.075
+@pytest.mark.parametrize("dim,Ns", [(1, (48, 64)), (2, (12, 16))])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_convtest_rates(dim, Ns, p):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    eL2, eH1 = [], []
+    for N in Ns:
+        o = OracleIGA(dim, 1)
+        for d in range(dim):
+            o.axis_uniform(d, p, N)
+            o.boundary_value(d, 0, 0, 0.0)
+            o.boundary_value(d, 1, 0, 0.0)
+        o.order(1)                                   # test/ConvTest.c:140-141
+        o.setup()
+        K, F = o.assemble("SYSTEM", "CONVTEST", [1.0, 1.0])
+        rp, ci, _ = o.pattern()
+        x = spla.spsolve(sp.csr_matrix((K.reshape(-1), ci, rp)).tocsc(), F.reshape(-1))
+        e = OracleIGA(dim, 1)                        # error norms with the 10-point rule (:186-189)
+        for d in range(dim):
+            e.axis_uniform(d, p, N)
+            e.rule_size(d, 10)
+        e.order(1)
+        e.setup()
+        l2 = e.error_norm(0, U=x, exact=4)[0]
+        h1s = e.error_norm(1, U=x, exact=4)[0]
+        eL2.append(l2)
+        eH1.append(np.sqrt(l2 ** 2 + h1s ** 2))
+    h = 1.0 / np.array(Ns, dtype=float)
+    rL2 = np.polyfit(np.log10(h), np.log10(eL2), 1)[0]
+    rH1 = np.polyfit(np.log10(h), np.log10(eH1), 1)[0]
+    assert (p + 1) - rL2 < 0.075 and p - rH1 < 0.075, (rL2, rH1)      # checkrate() of test/ConvTest.py:72-73
