@@ -177,6 +177,7 @@ PetscErrorCode IGAComputeErrorNorm(IGA iga, PetscInt k, Vec vecU, IGAFormExact E
 PetscErrorCode IGAGetInfoArray(IGA iga, PetscInt info[46]);     /* same layout as the oracle's oiga_get_info */
 PetscErrorCode IGAGetBasisTable(IGA iga, PetscInt axis, PetscInt which, PetscReal *out);  /* 0 value,1 weight,2 point,3 detJac,4 knots */
 PetscErrorCode IGAGetLGMapHost(IGA iga, PetscInt *lgmap);
+PetscErrorCode IGAGetOwnedNaturalIndices(IGA iga, PetscInt *nat);   /* [owned nodes]: the natural<->global map of IGAReadVec (src/petigavec.c n2g) */
 PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* forwarded to petiga_cuda_set_option; "async" = 1:
                                                                                  IGACompute* only enqueue on the IGA's stream (device-
                                                                                  resident hand-off to a GPU solve) */

@@ -938,6 +938,17 @@ static void owned_natural(IGA g, std::vector<size_t>& nat) {
     nat.push_back((size_t)(ls[0] + i) + n0 * ((size_t)(ls[1] + j) + n1 * (size_t)(ls[2] + k)));
 }
 
+// natural (i fastest over the global node grid) index of every owned node, in this rank's owned = PETSc-global order
+PetscErrorCode IGAGetOwnedNaturalIndices(IGA g, PetscInt* nat) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!nat) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  std::vector<size_t> v;
+  owned_natural(g, v);
+  for (size_t a = 0; a < v.size(); a++) nat[a] = (PetscInt)v[a];
+  return 0;
+}
+
 // IGAReadVec -> IGALoadVec (src/petigaio.c:685-709, :644-662): file holds the natural vector; every rank reads its part
 PetscErrorCode IGAReadVec(IGA g, Vec vec, const char filename[]) {
   if (PetscErrorCode e = check(g)) return e;

@@ -289,6 +289,13 @@ class IGA:
     def ComputeIJacobian(self, a, V, t, U, J):
         _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(J.h)))
 
+    def GetOwnedNaturalIndices(self):
+        inf = self.info()
+        n = int(np.prod(inf["node_lwidth"]))
+        out = np.empty(n, dtype=np.int32)
+        _chk(self.H.IGAGetOwnedNaturalIndices(self.h, out.ctypes.data_as(_ip)))
+        return out
+
     def Synchronize(self):
         _chk(self.H.IGASynchronize(self.h))
 

@@ -161,3 +161,31 @@ def test_gpu_assembly_on_loaded_geometry_and_vec_io(tmp_path):
     out = str(tmp_path / "v.dat")
     g.WriteVec(v, out)
     assert open(out, "rb").read() == open(VEC, "rb").read()
+
+
+@pytest.mark.parametrize("dim,N,size", [(2, (7, 5), 2), (2, (8, 8), 4), (3, (5, 4, 6), 8), (3, (6, 6, 6), 3)])
+def test_natural_to_global_map_of_readvec(dim, N, size):
+    """IGAReadVec places entry `natural` of the file into owned slot a: check that map against the rank's own numbering
+    (lgmap of the ghost box, itself bit-exact vs the oracle in test_host_layout.py) for every rank of several partitions."""
+    import petiga_b200 as pb
+    seen = []
+    start = 0
+    for rank in range(size):
+        g = pb.IGA(dim, 1, rank=rank, size=size)
+        for d in range(dim):
+            g.AxisInitUniform(d, 2, N[d])
+        g.SetUp()
+        inf = g.info()
+        nat = g.GetOwnedNaturalIndices()
+        gs, gw = inf["node_gstart"], inf["node_gwidth"]
+        ls, lw = inf["node_lstart"], inf["node_lwidth"]
+        nnp = inf["nnp"]
+        lg = g.lgmap().reshape(gw[2], gw[1], gw[0])
+        for k in range(ls[2], ls[2] + lw[2]):
+            for j in range(ls[1], ls[1] + lw[1]):
+                for i in range(ls[0], ls[0] + lw[0]):
+                    glob = lg[k - gs[2], j - gs[1], i - gs[0]]
+                    assert nat[glob - start] == i + nnp[0] * (j + nnp[1] * k)
+        start += len(nat)
+        seen.extend(nat.tolist())
+    assert sorted(seen) == list(range(int(np.prod([inf["nnp"][d] for d in range(3)]))))      # every natural entry lands exactly once
