@@ -561,7 +561,9 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
           fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
         }
         if (fs.vcount || fs.lcount) kp.any_bc = 1;
-        if (fs.lcount && P->d_X && L.dim > 1 && !L.ax[d].periodic) {   // BoundaryArea on a mapped face (petigaelem.c:1132-1162)
+        const int face_e = s ? L.ax[d].nel - 1 : 0;
+        const bool touches = face_e >= L.ax[d].es && face_e < L.ax[d].es + L.ax[d].ew;   // only ranks whose element box reaches the face
+        if (fs.lcount && P->d_X && L.dim > 1 && !L.ax[d].periodic && touches) {   // BoundaryArea on a mapped face (petigaelem.c:1132-1162)
           int fa[2] = {0, 0}, nfa = 0;
           for (int i = 0; i < L.dim; i++) if (i != d) fa[nfa++] = i;
           const int n0 = L.ax[fa[0]].ew, n1 = (L.dim > 2) ? L.ax[fa[1]].ew : 1;

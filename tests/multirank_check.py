@@ -46,6 +46,9 @@ def main():
         ("boundary integral", Case(3, p=2, N=6, bcv=[(0, 0, 0, 1.0)], bcf=[(d, s) for d in range(3) for s in range(2)]), "SYSTEM", "BOUNDARYINTEGRAL", [], False),
         ("boundary int mapped", Case(2, p=3, N=(9, 8), geometry=("perturbed", 0.05), bcv=[(1, 0, 0, 1.0)], bcf=[(0, 0), (0, 1), (1, 1)]), "SYSTEM", "BOUNDARYINTEGRAL", [], False),
         ("neumann demo", Case(2, p=2, N=(12, 10), bcl=[(d, s, 0, (2 * s - 1) * 6.283185307179586) for d in range(2) for s in range(2)]), "SYSTEM", "NEUMANN", [], False),
+        ("mapped loads", Case(3, dof=3, p=2, N=(6, 5, 6), order=1, geometry=("perturbed", 0.05), bcv=[(0, 0, c, 0.0) for c in range(3)],
+                              bcl=[(0, 1, 0, 1.0), (1, 0, 2, -0.5), (2, 1, 0, 0.25)]), "SYSTEM", "ELASTICITY", [1.0, 1.0], False),
+        ("cahnhilliard3d IJ", Case(3, p=2, N=8, C=1, periodic=True, order=2), "IJACOBIAN", "CAHNHILLIARD3D", [1.5, 1.0, 0.0117], True),
         ("cahnhilliard IJ", Case(2, p=2, N=32, C=1, periodic=True), "IJACOBIAN", "CAHNHILLIARD2D", [1.5, 3000.0], True),
         ("cahnhilliard IF", Case(2, p=2, N=32, C=1, periodic=True), "IFUNCTION", "CAHNHILLIARD2D", [1.5, 3000.0], True),
         ("bratu F", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "FUNCTION", "BRATU", [6.8], True),
