@@ -164,3 +164,32 @@ def test_hot_kernel_register_budget():
     assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4ELi4") <= 64
     assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi1ELi3") <= 64
     assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi3ELi0") <= 85      # cfg 4 (BAIJ bs=3): 3 CTAs per SM; 122 registers cost 43 %
+
+
+def test_functional_and_boundary_form_argument_checks():
+    """Argument / state checks of the added drivers follow the reference (no GPU needed: they fire before any device work)."""
+    import ctypes as C
+    g = pb.IGA(2, 1)
+    g.AxisInitUniform(0, 2, 4)
+    g.AxisInitUniform(1, 2, 4)
+    with pytest.raises(pb.IGAError) as e:
+        g.ComputeErrorNorm(0)                       # IGACheckSetUp (petigacomp.c:164)
+    assert e.value.code == 73
+    g.SetUp()
+    with pytest.raises(pb.IGAError) as e:
+        g.ComputeErrorNorm(-1)                      # "Derivative index must be nonnegative" (petigacomp.c:170)
+    assert e.value.code == 63
+    for axis, side in ((3, 0), (-1, 0), (0, 2), (0, -1)):
+        with pytest.raises(pb.IGAError) as e:
+            g.SetBoundaryForm(axis, side, True)     # IGAFormCheckArg (petigaform.c:95-99)
+        assert e.value.code == 63
+    # a host callback cannot run on the device: PETSC_ERR_SUP, never a silent CPU fallback
+    CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+    host_cb = CB(lambda p, U, n, S, ctx: 0)
+    S = (C.c_double * 3)()
+    rc = g.H.IGAComputeScalar(g.h, None, 3, S, host_cb, None)
+    assert rc == 56
+    EX = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+    out = (C.c_double * 1)()
+    rc = g.H.IGAComputeErrorNorm(g.h, 0, None, EX(lambda p, k, V, ctx: 0), out, None)
+    assert rc == 56
