@@ -130,6 +130,12 @@ PetscErrorCode IGAAxisSetPeriodic(IGAAxis axis, PetscBool periodic);
 PetscErrorCode IGAAxisSetDegree(IGAAxis axis, PetscInt p);
 PetscErrorCode IGAAxisSetKnots(IGAAxis axis, PetscInt m, const PetscReal U[]);
 PetscErrorCode IGAAxisInitUniform(IGAAxis axis, PetscInt N, PetscReal Ui, PetscReal Uf, PetscInt C);
+PetscErrorCode IGAAxisInitBreaks(IGAAxis axis, PetscInt nu, const PetscReal u[], PetscInt C);   /* src/petigaaxis.c:323-382 */
+PetscErrorCode IGAAxisGetPeriodic(IGAAxis axis, PetscBool *periodic);
+PetscErrorCode IGAAxisGetDegree(IGAAxis axis, PetscInt *p);
+PetscErrorCode IGAAxisGetKnots(IGAAxis axis, PetscInt *m, PetscReal *U[]);
+PetscErrorCode IGAAxisGetLimits(IGAAxis axis, PetscReal *Ui, PetscReal *Uf);
+PetscErrorCode IGAAxisGetSpans(IGAAxis axis, PetscInt *nel, PetscInt *span[]);
 PetscErrorCode IGAAxisGetSizes(IGAAxis axis, PetscInt *nel, PetscInt *nnp);
 
 /* ---- boundary conditions and forms: include/petiga.h:297-308 ---- */

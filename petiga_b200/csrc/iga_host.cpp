@@ -439,6 +439,52 @@ PetscErrorCode IGAAxisSetKnots(IGAAxis ax, PetscInt m, const PetscReal U[]) {
   axis_finish(ax);
   return 0;
 }
+// src/petigaaxis.c:323-382: open knot vector through the given breaks, each interior break repeated p-C times
+PetscErrorCode IGAAxisInitBreaks(IGAAxis ax, PetscInt nu, const PetscReal u[], PetscInt C) {
+  if (!ax || !u) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (C == PETSC_DECIDE) C = ax->p - 1;
+  if (ax->p < 1) return fail(PETSC_ERR_ORDER, "Must call IGAAxisSetDegree() first");
+  if (nu < 2) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Number of breaks must be at least two");
+  for (int i = 1; i < nu; i++) if (u[i - 1] >= u[i]) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Break sequence must be strictly increasing");
+  if (C < 0 || C >= ax->p) return fail(PETSC_ERR_ARG_WRONG, "Continuity must be in range [0,p-1]");
+  const int p = ax->p, s = p - C, r = nu - 1, m = 2 * (p + 1) + (r - 1) * s - 1, n = m - p - 1;
+  ax->m = m;
+  ax->U.assign(m + 1, 0.0);
+  double* U = ax->U.data();
+  int k = 0;
+  for (; k <= p; k++) { U[k] = u[0]; U[m - k] = u[r]; }
+  for (int i = 1; i <= r - 1; i++)
+    for (int j = 0; j < s; j++) U[k++] = u[i];
+  if (ax->periodic)
+    for (k = 0; k <= C; k++) { U[C - k] = U[p] - U[m - p] + U[n - k]; U[m - C + k] = U[m - p] - U[p] + U[p + 1 + k]; }
+  ax->nel = r;
+  ax->span.resize(r);
+  for (int i = 0; i < r; i++) ax->span[i] = p + i * s;
+  ax->nnp = ax->periodic ? n - C : n + 1;
+  return 0;
+}
+// getters: src/petigaaxis.c:155-310
+PetscErrorCode IGAAxisGetPeriodic(IGAAxis ax, PetscBool* periodic) { if (!ax || !periodic) return fail(PETSC_ERR_ARG_NULL, "Null pointer"); *periodic = ax->periodic ? PETSC_TRUE : PETSC_FALSE; return 0; }
+PetscErrorCode IGAAxisGetDegree(IGAAxis ax, PetscInt* p) { if (!ax || !p) return fail(PETSC_ERR_ARG_NULL, "Null pointer"); *p = ax->p; return 0; }
+PetscErrorCode IGAAxisGetKnots(IGAAxis ax, PetscInt* m, PetscReal* U[]) {
+  if (!ax) return fail(PETSC_ERR_ARG_NULL, "Null axis");
+  if (m) *m = ax->m;
+  if (U) *U = ax->U.data();
+  return 0;
+}
+PetscErrorCode IGAAxisGetLimits(IGAAxis ax, PetscReal* Ui, PetscReal* Uf) {
+  if (!ax) return fail(PETSC_ERR_ARG_NULL, "Null axis");
+  if (Ui) *Ui = ax->U[ax->p];
+  if (Uf) *Uf = ax->U[ax->m - ax->p];
+  return 0;
+}
+PetscErrorCode IGAAxisGetSpans(IGAAxis ax, PetscInt* nel, PetscInt* span[]) {
+  if (!ax) return fail(PETSC_ERR_ARG_NULL, "Null axis");
+  if (nel) *nel = ax->nel;
+  if (span) *span = ax->span.data();
+  return 0;
+}
+
 PetscErrorCode IGAAxisInitUniform(IGAAxis ax, PetscInt N, PetscReal Ui, PetscReal Uf, PetscInt C) {
   if (!ax) return fail(PETSC_ERR_ARG_NULL, "Null axis");
   if (C == PETSC_DECIDE) C = ax->p - 1;

@@ -214,6 +214,25 @@ class IGA:
         _chk(self.H.IGAAxisSetDegree(ax, p))
         _chk(self.H.IGAAxisSetKnots(ax, len(U) - 1, U.ctypes.data_as(_dp)))
 
+    def AxisInitBreaks(self, i, p, breaks, C_=-1, periodic=False):
+        ax = self._axis(i)
+        u = np.ascontiguousarray(breaks, dtype=np.float64)
+        _chk(self.H.IGAAxisSetPeriodic(ax, int(periodic)))
+        _chk(self.H.IGAAxisSetDegree(ax, p))
+        _chk(self.H.IGAAxisInitBreaks(ax, len(u), u.ctypes.data_as(_dp), C_))
+
+    def AxisGetKnots(self, i):
+        ax = self._axis(i)
+        m, U = C.c_int(), _dp()
+        _chk(self.H.IGAAxisGetKnots(ax, C.byref(m), C.byref(U)))
+        return np.ctypeslib.as_array(U, shape=(m.value + 1,)).copy()
+
+    def AxisGetSpans(self, i):
+        ax = self._axis(i)
+        n, sp = C.c_int(), _ip()
+        _chk(self.H.IGAAxisGetSpans(ax, C.byref(n), C.byref(sp)))
+        return np.ctypeslib.as_array(sp, shape=(n.value,)).copy()
+
     # oracle-compatible aliases so that fixtures can build either object
     def axis_uniform(self, axis, p, N, Ui=0.0, Uf=1.0, C=-1, periodic=False):
         self.AxisInitUniform(axis, p, N, Ui, Uf, C, periodic)

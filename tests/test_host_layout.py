@@ -193,3 +193,37 @@ def test_functional_and_boundary_form_argument_checks():
     out = (C.c_double * 1)()
     rc = g.H.IGAComputeErrorNorm(g.h, 0, None, EX(lambda p, k, V, ctx: 0), out, None)
     assert rc == 56
+
+
+@pytest.mark.parametrize("p,C,periodic", [(2, 1, False), (3, 0, False), (3, 2, True), (4, 1, False)])
+def test_axis_init_breaks_matches_oracle_tables(p, C, periodic):
+    """IGAAxisInitBreaks (src/petigaaxis.c:323-382) on a graded mesh: knots, spans and the 1-D basis tables of the mirror are
+    bit-identical to the oracle's built from the same knot vector; uniform breaks reproduce IGAAxisInitUniform bit for bit."""
+    from oracle.oracle import OracleIGA
+    breaks = np.array([0.0, 0.1, 0.25, 0.3, 0.55, 0.7, 0.85, 0.9, 1.0]) ** 1.5
+    g = pb.IGA(1, 1)
+    g.AxisInitBreaks(0, p, breaks, C, periodic)
+    U = g.AxisGetKnots(0)
+    s = p - C
+    assert len(U) == 2 * (p + 1) + (len(breaks) - 2) * s                      # m + 1
+    assert np.array_equal(np.unique(U[p:len(U) - p]), breaks)
+    assert np.array_equal(g.AxisGetSpans(0), p + s * np.arange(len(breaks) - 1))
+    g.SetUp()
+    o = OracleIGA(1, 1)
+    o.axis_knots(0, p, U, periodic)
+    o.setup()
+    to, tg = o.tables(0), g.tables(0)
+    for key in ("U", "detJac", "weight", "point", "value"):
+        assert np.array_equal(np.asarray(to[key]), np.asarray(tg[key])), key
+    assert g.info()["nnp"][0] == o.info()["nnp"][0] and g.info()["nel"][0] == len(breaks) - 1
+    # uniform breaks: identical to IGAAxisInitUniform when the breaks are the values it computes
+    N = 7
+    gu = pb.IGA(1, 1)
+    gu.AxisInitUniform(0, p, N, 0.5, 2.0, C, periodic)
+    Uu = gu.AxisGetKnots(0)
+    gb = pb.IGA(1, 1)
+    gb.AxisInitBreaks(0, p, np.unique(Uu[p:len(Uu) - p]), C, periodic)
+    assert np.array_equal(gb.AxisGetKnots(0), Uu)
+    with pytest.raises(pb.IGAError) as e:
+        gb.AxisInitBreaks(0, p, [0.0, 0.5, 0.5, 1.0], C)        # strictly increasing (petigaaxis.c:337-339)
+    assert e.value.code == 63
