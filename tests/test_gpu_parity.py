@@ -187,6 +187,36 @@ def test_nurbs_quarter_annulus(form, params):
         assert abs(A.values().sum() - np.pi * 3 / 4) < 1e-6
 
 
+# ---- graded (non-uniform) meshes through IGAAxisInitBreaks: the separable path's 1-D matrices are per node, not per mesh ----
+@pytest.mark.parametrize("dim,p", [(2, 2), (3, 3)])
+def test_graded_mesh_init_breaks(dim, p):
+    import petiga_b200 as pb
+    from oracle.oracle import OracleIGA
+    from tests.common import rel_frobenius
+    brk = [np.linspace(0.0, 1.0, 9 + d) ** (1.3 + 0.4 * d) for d in range(dim)]
+    g = pb.IGA(dim, 1)
+    o = OracleIGA(dim, 1)
+    for d in range(dim):
+        g.AxisInitBreaks(d, p, brk[d])
+        o.axis_knots(d, p, g.AxisGetKnots(d))
+        for s in range(2):
+            g.SetBoundaryValue(d, s, 0, 0.5 + d)
+            o.boundary_value(d, s, 0, 0.5 + d)
+    g.SetUp()
+    o.setup()
+    Ko, Fo = o.assemble("SYSTEM", "POISSON")
+    rpo, cio, _ = o.pattern()
+    for path in (0, 1):
+        g.SetOption("path", path)
+        g.SetForm("SYSTEM", "POISSON")
+        A, B = g.CreateMat(), g.CreateVec()
+        g.ComputeSystem(A, B)
+        rp, ci = A.pattern()
+        assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+        assert rel_frobenius(A.values(), Ko.reshape(-1)) <= TOL and rel_frobenius(B.get(), Fo.reshape(-1)) <= TOL
+        assert int(g.GetStat("last_path")) == (2 if path == 0 else 1)
+
+
 # ---- CahnHilliard3D (demo/CahnHilliard3D.c): order-2 form with state in 3-D, periodic, both quadrature kernels ----------
 @pytest.mark.parametrize("p,N", [(2, 6), (3, 8)])
 def test_cahnhilliard3d(p, N):
