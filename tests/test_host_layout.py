@@ -227,3 +227,22 @@ def test_axis_init_breaks_matches_oracle_tables(p, C, periodic):
     with pytest.raises(pb.IGAError) as e:
         gb.AxisInitBreaks(0, p, [0.0, 0.5, 0.5, 1.0], C)        # strictly increasing (petigaaxis.c:337-339)
     assert e.value.code == 63
+
+
+def test_headers_are_plain_c_and_the_readme_example_links(tmp_path):
+    """include/*.h are the C boundary: a C99 translation unit (tests/csrc/readme_example.c, the README's snippet) must compile
+    and link against the two shared libraries with gcc.  Without a GPU it stops at IGACreateMat with an error code (exit 3) --
+    there is no CPU fallback; on a GPU box it runs through (exit 0)."""
+    import shutil
+    import subprocess
+    import petiga_b200
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "readme_example")
+    lib = petiga_b200.lib_dir()
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "csrc", "readme_example.c"),
+                           "-L", lib, "-lpetiga_host", "-lpetiga_cuda", "-Wl,-rpath," + lib, "-o", exe])
+    rc = subprocess.run([exe]).returncode
+    import torch
+    assert rc == (0 if torch.cuda.is_available() else 3)
