@@ -54,6 +54,7 @@ typedef struct { int rank, size; void *nccl; int device; } IGAComm;   /* stands 
 typedef struct _p_IGA *IGA;
 typedef struct _n_IGAAxis *IGAAxis;
 typedef struct _n_IGAPoint *IGAPoint;       /* opaque here: forms run on the device */
+typedef struct _n_IGAForm *IGAForm;         /* include/petiga.h:220-268; opaque handle of the IGA's form */
 typedef struct _p_Mat *Mat;
 typedef struct _p_Vec *Vec;
 
@@ -150,6 +151,20 @@ PetscErrorCode IGASetFormFunction(IGA iga, IGAFormFunction Function, void *ctx);
 PetscErrorCode IGASetFormJacobian(IGA iga, IGAFormJacobian Jacobian, void *ctx);
 PetscErrorCode IGASetFormIFunction(IGA iga, IGAFormIFunction IFunction, void *ctx);
 PetscErrorCode IGASetFormIJacobian(IGA iga, IGAFormIJacobian IJacobian, void *ctx);
+
+/* the IGAForm object API of the demos that use it (demo/BoundaryIntegral.c:163-172): include/petiga.h:270-289 */
+PetscErrorCode IGAGetForm(IGA iga, IGAForm *form);
+PetscErrorCode IGAFormSetBoundaryValue(IGAForm form, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value);
+PetscErrorCode IGAFormSetBoundaryLoad(IGAForm form, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value);
+PetscErrorCode IGAFormSetBoundaryForm(IGAForm form, PetscInt axis, PetscInt side, PetscBool flag);
+PetscErrorCode IGAFormClearBoundary(IGAForm form, PetscInt axis, PetscInt side);
+PetscErrorCode IGAFormSetVector(IGAForm form, IGAFormVector Vector, void *ctx);
+PetscErrorCode IGAFormSetMatrix(IGAForm form, IGAFormMatrix Matrix, void *ctx);
+PetscErrorCode IGAFormSetSystem(IGAForm form, IGAFormSystem System, void *ctx);
+PetscErrorCode IGAFormSetFunction(IGAForm form, IGAFormFunction Function, void *ctx);
+PetscErrorCode IGAFormSetJacobian(IGAForm form, IGAFormJacobian Jacobian, void *ctx);
+PetscErrorCode IGAFormSetIFunction(IGAForm form, IGAFormIFunction IFunction, void *ctx);
+PetscErrorCode IGAFormSetIJacobian(IGAForm form, IGAFormIJacobian IJacobian, void *ctx);
 
 /* ---- Mat / Vec: src/petigamat.c:345-549, src/petigavec.c:78-113 ---- */
 PetscErrorCode IGACreateMat(IGA iga, Mat *mat);

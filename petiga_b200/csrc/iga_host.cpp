@@ -644,6 +644,35 @@ static PetscErrorCode set_bc_entry(IGA g, PetscInt axis, PetscInt side, PetscInt
 }
 PetscErrorCode IGASetBoundaryValue(IGA g, PetscInt a, PetscInt s, PetscInt f, PetscScalar v) { return set_bc_entry(g, a, s, f, v, false); }
 PetscErrorCode IGASetBoundaryLoad(IGA g, PetscInt a, PetscInt s, PetscInt f, PetscScalar v) { return set_bc_entry(g, a, s, f, v, true); }
+// IGAForm object API (include/petiga.h:270-289, src/petigaform.c): in the mirror the form lives inside the IGA, so the handle
+// is the IGA itself behind an opaque type; every function forwards to the IGASet* entry of the same meaning
+static inline IGA form_iga(IGAForm f) { return reinterpret_cast<IGA>(f); }
+PetscErrorCode IGAGetForm(IGA g, IGAForm* form) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!form) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  *form = reinterpret_cast<IGAForm>(g);
+  return 0;
+}
+PetscErrorCode IGAFormSetBoundaryValue(IGAForm f, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value) { return IGASetBoundaryValue(form_iga(f), axis, side, field, value); }
+PetscErrorCode IGAFormSetBoundaryLoad(IGAForm f, PetscInt axis, PetscInt side, PetscInt field, PetscScalar value) { return IGASetBoundaryLoad(form_iga(f), axis, side, field, value); }
+PetscErrorCode IGAFormSetBoundaryForm(IGAForm f, PetscInt axis, PetscInt side, PetscBool flag) { return IGASetBoundaryForm(form_iga(f), axis, side, flag); }
+PetscErrorCode IGAFormClearBoundary(IGAForm f, PetscInt axis, PetscInt side) {   // src/petigaform.c: value/load counts and the visit flag of one face
+  IGA g = form_iga(f);
+  if (PetscErrorCode e = check(g)) return e;
+  if (axis < 0 || axis >= 3 || side < 0 || side >= 2) return fail(PETSC_ERR_ARG_OUTOFRANGE, "axis/side out of range");
+  g->bc.vcount[axis][side] = 0; g->bc.lcount[axis][side] = 0; g->visit[axis][side] = 0;
+  g->bc_dirty = true;
+  if (g->plan) return from_cuda(petiga_cuda_set_boundary_form(g->plan, axis, side, 0));
+  return 0;
+}
+PetscErrorCode IGAFormSetVector(IGAForm f, IGAFormVector fn, void* ctx) { return IGASetFormVector(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetMatrix(IGAForm f, IGAFormMatrix fn, void* ctx) { return IGASetFormMatrix(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetSystem(IGAForm f, IGAFormSystem fn, void* ctx) { return IGASetFormSystem(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetFunction(IGAForm f, IGAFormFunction fn, void* ctx) { return IGASetFormFunction(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetJacobian(IGAForm f, IGAFormJacobian fn, void* ctx) { return IGASetFormJacobian(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetIFunction(IGAForm f, IGAFormIFunction fn, void* ctx) { return IGASetFormIFunction(form_iga(f), fn, ctx); }
+PetscErrorCode IGAFormSetIJacobian(IGAForm f, IGAFormIJacobian fn, void* ctx) { return IGASetFormIJacobian(form_iga(f), fn, ctx); }
+
 // include/petiga.h:300, src/petigaform.c IGAFormSetBoundaryForm
 PetscErrorCode IGASetBoundaryForm(IGA g, PetscInt axis, PetscInt side, PetscBool flag) {
   if (PetscErrorCode e = check(g)) return e;

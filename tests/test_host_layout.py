@@ -241,8 +241,9 @@ def test_headers_are_plain_c_and_the_readme_example_links(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "readme_example")
     lib = petiga_b200.lib_dir()
-    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "csrc", "readme_example.c"),
-                           "-L", lib, "-lpetiga_host", "-lpetiga_cuda", "-Wl,-rpath," + lib, "-o", exe])
-    rc = subprocess.run([exe]).returncode
     import torch
-    assert rc == (0 if torch.cuda.is_available() else 3)
+    for src in ("readme_example.c", "boundary_integral_example.c"):     # the second follows demo/BoundaryIntegral.c's main()
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "csrc", src),
+                               "-L", lib, "-lpetiga_host", "-lpetiga_cuda", "-Wl,-rpath," + lib, "-o", exe])
+        rc = subprocess.run([exe]).returncode
+        assert rc == (0 if torch.cuda.is_available() else 3), (src, rc)
