@@ -78,7 +78,7 @@ class ClockSampler:
 
 
 def build_case(mesh, p=3, geometry=None):
-    from tests.common import Case
+    from petiga_b200.cases import Case
     geo = None if geometry in (None, "identity") else ("perturbed", 0.05)     # SURVEY 8d cfg 2g
     return Case(3, p=p, N=mesh, bcv=[(d, s, 0, 1.0) for d in range(3) for s in range(2)], geometry=geo)
 

@@ -157,6 +157,7 @@ int petiga_cuda_set_boundary_form(petiga_cuda_plan *plan, int axis, int side, in
 /* IGASetFixTable with the table as a *global device vector* (this rank's owned part [owned nodes * dof]): the library does
    the global-to-local scatter itself (NCCL halo on more than one rank).  Call after petiga_cuda_set_bc; NULL clears it. */
 int petiga_cuda_set_fixtable_device(petiga_cuda_plan *plan, const double *table_own);
+/* form_id = -1 clears the slot (IGASetForm*(iga, NULL, NULL)); compute on it then fails with PETIGA_CUDA_ERR_ORDER */
 int petiga_cuda_form_select(petiga_cuda_plan *plan, int slot, int form_id, const double *params, int nparams);
 
 /* ---- pattern (IGACreateMat) ----
@@ -191,7 +192,9 @@ int petiga_cuda_compute_scalar(petiga_cuda_plan *plan, int scalar_id, const doub
 int petiga_cuda_compute_host(petiga_cuda_plan *plan, int slot, int block, double shift, const double *V_host,
                              double t, const double *U_host, double *values_host, double *rhs_host);
 
-/* ---- device memory helpers for C callers without a CUDA runtime of their own ---- */
+/* ---- device memory helpers for C callers without a CUDA runtime of their own.  They act on the CURRENT device:
+        petiga_cuda_plan_activate makes the plan's device current (cudaSetDevice) ---- */
+int petiga_cuda_plan_activate(petiga_cuda_plan *plan);
 int petiga_cuda_malloc(void **ptr, size_t bytes);
 int petiga_cuda_free(void *ptr);
 int petiga_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);

@@ -7,3 +7,4 @@ compute call goes through the CUDA library and fails loudly when it (or a GPU) i
 """
 from .build import build, lib_dir  # noqa: F401
 from .iga import IGA, IGAError, Mat, Vec, FORMS, iga_partition, load_host, load_cuda  # noqa: F401
+from .cases import Case, baseline_config, state_vectors  # noqa: F401

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -41,10 +42,12 @@ struct _n_IGAAxis {
   IGA owner = nullptr;
 };
 
+// Mat/Vec borrow plan-owned device tables (the CSR pattern); `gen` is the IGA's plan generation at creation, so that a Mat or
+// Vec that outlives its set-up (IGARead, IGASetRuleSize, IGADestroy) is refused instead of reading freed device memory.
 struct _p_Vec {
-  IGA iga; int n; double* d; };
+  IGA iga; int n; double* d; long gen; };
 struct _p_Mat {
-  IGA iga; int baij; int bs; int nrows; int64_t nnz; const int* d_rowptr; const int* d_colidx; double* d_values; };
+  IGA iga; int baij; int bs; int nrows; int64_t nnz; const int* d_rowptr; const int* d_colidx; double* d_values; long gen; };
 
 struct _p_IGA {
   IGAComm comm;
@@ -77,9 +80,23 @@ struct _p_IGA {
   int visit[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // IGASetBoundaryForm
   std::vector<double> bnd_value[3][2]; double bnd_point[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // IGABasis.bnd_* (petigabasis.c:208-217)
   bool async = false;   // IGASetOption("async",1): the drivers only enqueue; IGASynchronize / host getters wait
+  long plan_gen = 0;    // bumped whenever the plan is destroyed (Mat/Vec created before that become stale)
 };
 
 namespace {
+
+std::set<IGA>& live_igas() { static std::set<IGA> s; return s; }
+void drop_plan(IGA g) {
+  if (g->plan) { petiga_cuda_plan_destroy(g->plan); g->plan = nullptr; }
+  g->plan_gen++;
+}
+template <class Obj>
+PetscErrorCode check_owner(Obj* o, IGA g, const char* what) {
+  if (!live_igas().count(o->iga)) return fail(PETSC_ERR_ARG_WRONGSTATE, std::string(what) + ": its IGA was destroyed");
+  if (g && o->iga != g) return fail(PETSC_ERR_ARG_WRONG, std::string(what) + " was created by a different IGA");            // PetscCheckSameComm-style
+  if (o->gen != o->iga->plan_gen) return fail(PETSC_ERR_ARG_WRONGSTATE, std::string(what) + " predates the current IGASetUp(); create it again");
+  return 0;
+}
 
 // ---- knots ----
 int next_knot(int m, const double* U, int k, int dir) {
@@ -283,13 +300,13 @@ const FormEntry* lookup_form(const void* fn, int slot) {
 
 PetscErrorCode set_form(IGA g, int slot, const void* fn, void* ctx) {
   if (PetscErrorCode e = check(g)) return e;
-  if (!fn) { g->slots[slot].form = -1; return 0; }
+  auto& s = g->slots[slot];
+  if (!fn) { s.form = -1; s.nprm = 0; s.dirty = true; return 0; }   // a cleared callback reaches the plan too (form_select(-1))
   const FormEntry* fe = lookup_form(fn, slot);
   if (!fe) return fail(PETSC_ERR_SUP, "IGASetForm*: host callbacks cannot run on the GPU; pass one of the IGADeviceForm_* sentinels");
-  auto& s = g->slots[slot];
+  if (fe->nprm && !ctx) return fail(PETSC_ERR_ARG_NULL, "IGASetForm*: this form needs its AppCtx");   // nothing committed yet
   s.form = fe->form; s.nprm = fe->nprm; s.dirty = true;
   memset(s.prm, 0, sizeof(s.prm));
-  if (fe->nprm && !ctx) return fail(PETSC_ERR_ARG_NULL, "IGASetForm*: this form needs its AppCtx");
   for (int k = 0; k < fe->nprm; k++) s.prm[k] = ((const double*)ctx)[k];
   if (fe->swap01) std::swap(s.prm[0], s.prm[1]);   // demo/Elasticity.c AppCtx is {mu, lambda}
   return 0;
@@ -357,6 +374,7 @@ PetscErrorCode IGACreate(IGAComm comm, IGA* iga) {
   g->comm = comm;
   memset(&g->bc, 0, sizeof(g->bc));
   for (int d = 0; d < 3; d++) g->axis[d].owner = g;
+  live_igas().insert(g);
   *iga = g;
   return 0;
 }
@@ -364,8 +382,9 @@ PetscErrorCode IGACreate(IGAComm comm, IGA* iga) {
 PetscErrorCode IGADestroy(IGA* iga) {
   if (!iga || !*iga) return 0;
   IGA g = *iga;
-  if (g->plan) petiga_cuda_plan_destroy(g->plan);
+  drop_plan(g);
   if (g->layout) petiga_layout_destroy(g->layout);
+  live_igas().erase(g);
   delete g;
   *iga = nullptr;
   return 0;
@@ -412,7 +431,7 @@ PetscErrorCode IGASetRuleSize(IGA g, PetscInt i, PetscInt nqp) {
   if (nqp < 1 || nqp > 10) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Number of quadrature points not implemented");
   g->rule_nqp[i] = nqp;
   g->setup = 0;   // IGASetRuleSize resets the setup stage in the reference
-  if (g->plan) { petiga_cuda_plan_destroy(g->plan); g->plan = nullptr; }
+  drop_plan(g);
   return 0;
 }
 PetscErrorCode IGASetMatType(IGA g, const char* t) {
@@ -700,7 +719,7 @@ PetscErrorCode IGACreateMat(IGA g, Mat* mat) {
   if (PetscErrorCode e = ensure_plan(g)) return e;
   const bool baij = g->mattype.empty() ? (g->dof > 1) : (g->mattype == "baij");   // src/petiga.c:1326-1330
   Mat A = new _p_Mat();
-  A->iga = g; A->baij = baij; A->bs = g->dof;
+  A->iga = g; A->baij = baij; A->bs = g->dof; A->gen = g->plan_gen;
   int nrows; int64_t nnz;
   int rc = petiga_cuda_plan_pattern(g->plan, baij ? 1 : 0, &nrows, &nnz, &A->d_rowptr, &A->d_colidx);
   if (rc) { delete A; return from_cuda(rc); }
@@ -708,6 +727,7 @@ PetscErrorCode IGACreateMat(IGA g, Mat* mat) {
   int nown, ng; int64_t nnzb;
   petiga_cuda_plan_sizes(g->plan, &nown, &ng, &nnzb);
   const size_t nval = (size_t)nnzb * g->dof * g->dof;
+  petiga_cuda_plan_activate(g->plan);   // allocate on the plan's device, not on whichever is current
   rc = petiga_cuda_malloc((void**)&A->d_values, nval * sizeof(double));
   if (rc) { delete A; return from_cuda(rc); }
   *mat = A;
@@ -721,7 +741,8 @@ PetscErrorCode IGACreateVec(IGA g, Vec* vec) {
   int nown, ng; int64_t nnzb;
   petiga_cuda_plan_sizes(g->plan, &nown, &ng, &nnzb);
   Vec v = new _p_Vec();
-  v->iga = g; v->n = nown * g->dof;
+  v->iga = g; v->n = nown * g->dof; v->gen = g->plan_gen;
+  petiga_cuda_plan_activate(g->plan);
   int rc = petiga_cuda_malloc((void**)&v->d, (size_t)v->n * sizeof(double));
   if (rc) { delete v; return from_cuda(rc); }
   std::vector<double> z(v->n, 0.0);
@@ -740,8 +761,10 @@ PetscErrorCode MatGetSizesIGA(Mat A, PetscInt* nrows, int64_t* nnz, PetscInt* bs
 }
 PetscErrorCode MatGetCSRHost(Mat A, PetscInt* rowptr, PetscInt* colidx, PetscScalar* values) {
   if (!A) return fail(PETSC_ERR_ARG_NULL, "Null Mat");
+  if (PetscErrorCode e = check_owner(A, nullptr, "Mat")) return e;
   int rc = A->iga->plan ? petiga_cuda_finish(A->iga->plan) : 0;
   if (rc) return from_cuda(rc);
+  if (A->iga->plan) petiga_cuda_plan_activate(A->iga->plan);
   if (rowptr) rc = petiga_cuda_memcpy_d2h(rowptr, A->d_rowptr, ((size_t)A->nrows + 1) * sizeof(int));
   if (!rc && colidx) rc = petiga_cuda_memcpy_d2h(colidx, A->d_colidx, (size_t)A->nnz * sizeof(int));
   if (!rc && values) {
@@ -752,8 +775,8 @@ PetscErrorCode MatGetCSRHost(Mat A, PetscInt* rowptr, PetscInt* colidx, PetscSca
 }
 PetscErrorCode MatGetValuesDevice(Mat A, PetscScalar** d) { if (!A || !d) return fail(PETSC_ERR_ARG_NULL, "Null"); *d = A->d_values; return 0; }
 PetscErrorCode VecGetLocalSize(Vec v, PetscInt* n) { if (!v || !n) return fail(PETSC_ERR_ARG_NULL, "Null"); *n = v->n; return 0; }
-PetscErrorCode VecGetArrayHost(Vec v, PetscScalar* out) { if (!v || !out) return fail(PETSC_ERR_ARG_NULL, "Null"); if (v->iga->plan) petiga_cuda_finish(v->iga->plan); return from_cuda(petiga_cuda_memcpy_d2h(out, v->d, (size_t)v->n * sizeof(double))); }
-PetscErrorCode VecSetArrayHost(Vec v, const PetscScalar* in) { if (!v || !in) return fail(PETSC_ERR_ARG_NULL, "Null"); return from_cuda(petiga_cuda_memcpy_h2d(v->d, in, (size_t)v->n * sizeof(double))); }
+PetscErrorCode VecGetArrayHost(Vec v, PetscScalar* out) { if (!v || !out) return fail(PETSC_ERR_ARG_NULL, "Null"); if (PetscErrorCode e = check_owner(v, nullptr, "Vec")) return e; if (v->iga->plan) { petiga_cuda_finish(v->iga->plan); petiga_cuda_plan_activate(v->iga->plan); } return from_cuda(petiga_cuda_memcpy_d2h(out, v->d, (size_t)v->n * sizeof(double))); }
+PetscErrorCode VecSetArrayHost(Vec v, const PetscScalar* in) { if (!v || !in) return fail(PETSC_ERR_ARG_NULL, "Null"); if (PetscErrorCode e = check_owner(v, nullptr, "Vec")) return e; if (v->iga->plan) petiga_cuda_plan_activate(v->iga->plan); return from_cuda(petiga_cuda_memcpy_h2d(v->d, in, (size_t)v->n * sizeof(double))); }
 PetscErrorCode VecGetArrayDevice(Vec v, PetscScalar** d) { if (!v || !d) return fail(PETSC_ERR_ARG_NULL, "Null"); *d = v->d; return 0; }
 
 static PetscErrorCode run(IGA g, int slot, PetscReal a, Vec V, PetscReal t, Vec U, Mat A, Vec B) {
@@ -761,6 +784,8 @@ static PetscErrorCode run(IGA g, int slot, PetscReal a, Vec V, PetscReal t, Vec 
   if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");                     // IGACheckSetUp
   if (g->slots[slot].form < 0) return fail(PETSC_ERR_USER, "Must call IGASetForm*() first");
   if (PetscErrorCode e = ensure_plan(g)) return e;
+  if (A) if (PetscErrorCode e = check_owner(A, g, "Mat")) return e;
+  for (Vec x : {V, U, B}) if (x) if (PetscErrorCode e = check_owner(x, g, "Vec")) return e;
   int rc = petiga_cuda_compute(g->plan, slot, A ? A->baij : 0, a, V ? V->d : nullptr, t, U ? U->d : nullptr, A ? A->d_values : nullptr, B ? B->d : nullptr);
   if (rc) return from_cuda(rc);
   if (g->async) return 0;                          // device-resident hand-off: ordered on the IGA's stream, no host wait
@@ -904,7 +929,7 @@ struct BinFile {
 };
 
 void reset_iga(IGA g) {   // IGAReset (src/petiga.c) as far as the mirror holds state
-  if (g->plan) { petiga_cuda_plan_destroy(g->plan); g->plan = nullptr; }
+  drop_plan(g);
   if (g->layout) { petiga_layout_destroy(g->layout); g->layout = nullptr; }
   g->setup = 0;
   g->nsd = 0; g->geomX.clear(); g->geomW.clear(); g->geomW_all.clear(); g->rational = false; g->geom_dirty = true;

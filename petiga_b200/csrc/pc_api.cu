@@ -267,10 +267,17 @@ int petiga_cuda_plan_create(petiga_cuda_plan** plan, const petiga_cuda_space* sp
     if ((rc = upload<double>(P, nullptr, nl, &P->d_U_loc))) return bail(rc);
     if ((rc = upload<double>(P, nullptr, nl, &P->d_V_loc))) return bail(rc);
     std::vector<int> rows;
+    std::vector<int64_t> offs;      // prefix sum of the row lengths inside each peer's slab (the sender packs rows back to back)
     P->recv_row_off.clear();
-    for (auto& r : L.recv) { P->recv_row_off.push_back(rows.size()); rows.insert(rows.end(), r.rows.begin(), r.rows.end()); }
+    for (auto& r : L.recv) {
+      P->recv_row_off.push_back(rows.size());
+      rows.insert(rows.end(), r.rows.begin(), r.rows.end());
+      int64_t o = 0;
+      for (int row : r.rows) { offs.push_back(o); o += L.rowbase[row + 1] - L.rowbase[row]; }
+    }
     P->recv_row_off.push_back(rows.size());
     if ((rc = upload(P, rows.data(), rows.size(), &P->d_recv_rows))) return bail(rc);
+    if ((rc = upload(P, offs.data(), offs.size(), &P->d_recv_off))) return bail(rc);
   }
   cudaError_t e = cudaStreamSynchronize(P->stream);
   if (e != cudaSuccess) return bail(cuda_fail(e, "plan upload"));
@@ -349,7 +356,27 @@ int petiga_cuda_set_bc(petiga_cuda_plan* P, const petiga_cuda_bc* bc) {
       if (bc->vcount[d][s] < 0 || bc->vcount[d][s] > 64 || bc->lcount[d][s] < 0 || bc->lcount[d][s] > 64) return PETIGA_CUDA_ERR_ARG;
       if (d < P->L.dim && (bc->vcount[d][s] || bc->lcount[d][s])) P->has_bc = true;
     }
-  P->bc = *bc;
+  // copy with the semantics of IGAFormSetBoundaryValue/Load (src/petigaform.c:102-149): one entry per field, a repeated field
+  // overwrites the earlier value; negative fields are an argument error (PETSC_ERR_ARG_OUTOFRANGE there)
+  for (int d = 0; d < 3; d++)
+    for (int s = 0; s < 2; s++) {
+      for (int k = 0; k < bc->vcount[d][s]; k++) {
+        const int f = bc->vfield[d][s][k];
+        if (f < 0) { memset(&P->bc, 0, sizeof(P->bc)); P->has_bc = false; set_error("set_bc: negative field index"); return PETIGA_CUDA_ERR_ARG; }
+        int pos = -1;
+        for (int j = 0; j < P->bc.vcount[d][s]; j++) if (P->bc.vfield[d][s][j] == f) pos = j;
+        if (pos < 0) pos = P->bc.vcount[d][s]++;
+        P->bc.vfield[d][s][pos] = f; P->bc.vvalue[d][s][pos] = bc->vvalue[d][s][k];
+      }
+      for (int k = 0; k < bc->lcount[d][s]; k++) {
+        const int f = bc->lfield[d][s][k];
+        if (f < 0) { memset(&P->bc, 0, sizeof(P->bc)); P->has_bc = false; set_error("set_bc: negative field index"); return PETIGA_CUDA_ERR_ARG; }
+        int pos = -1;
+        for (int j = 0; j < P->bc.lcount[d][s]; j++) if (P->bc.lfield[d][s][j] == f) pos = j;
+        if (pos < 0) pos = P->bc.lcount[d][s]++;
+        P->bc.lfield[d][s][pos] = f; P->bc.lvalue[d][s][pos] = bc->lvalue[d][s][k];
+      }
+    }
   P->bc.fixtableU = nullptr;
   if (bc->fixtableU) {
     const size_t n = P->L.localrow.size() * P->L.dof;
@@ -388,6 +415,11 @@ int petiga_cuda_set_fixtable_device(petiga_cuda_plan* P, const double* table_own
 }
 
 int petiga_cuda_form_select(petiga_cuda_plan* P, int slot, int form_id, const double* params, int nparams) {
+  if (P && slot >= 0 && slot < PETIGA_NSLOTS && form_id == -1) {   // IGASetForm*(iga, NULL, NULL): the slot has no callback any more
+    P->slots[slot].form = -1;
+    P->config_version++;
+    return 0;
+  }
   if (!P || slot < 0 || slot >= PETIGA_NSLOTS || form_id < 0 || form_id >= PETIGA_NFORMS || nparams < 0 || nparams > 8) {
     set_error("form_select: bad slot / form / nparams");
     return PETIGA_CUDA_ERR_ARG;
@@ -552,12 +584,12 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
         FixSide& fs = kp.bc[d][s];
         for (int k = 0; k < P->bc.vcount[d][s]; k++) {
           int c = P->bc.vfield[d][s][k];
-          if (c >= L.dof) continue;   // AddFixa skips fields >= dof (petigaelem.c:1179)
+          if (c >= L.dof || fs.vcount >= kMaxDof) continue;   // AddFixa skips fields >= dof (petigaelem.c:1179)
           fs.vfield[fs.vcount] = c; fs.vvalue[fs.vcount] = P->bc.vvalue[d][s][k]; fs.vcount++;
         }
         for (int k = 0; k < P->bc.lcount[d][s]; k++) {
           int c = P->bc.lfield[d][s][k];
-          if (c >= L.dof) continue;
+          if (c >= L.dof || fs.lcount >= kMaxDof) continue;
           fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
         }
         if (fs.vcount || fs.lcount) kp.any_bc = 1;
@@ -692,7 +724,8 @@ int petiga_cuda_measure_fp64(int device, double seconds, double* tflops_burst, d
   return 0;
 }
 
-// ---- small device-memory helpers ----
+// ---- small device-memory helpers (they act on the current device: call petiga_cuda_plan_activate first) ----
+int petiga_cuda_plan_activate(petiga_cuda_plan* P) { if (!P) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaSetDevice(P->device)); return 0; }
 int petiga_cuda_malloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaMalloc(ptr, bytes ? bytes : 1)); return 0; }
 int petiga_cuda_free(void* ptr) { PC_CUDA(cudaFree(ptr)); return 0; }
 int petiga_cuda_memcpy_h2d(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }

@@ -220,7 +220,7 @@ int launch_boundary_pass(petiga_cuda_plan* P, int slot, int form, const double* 
             FixSide& fs = bp.bc[dd][ss];
             for (int k = 0; k < P->bc.vcount[dd][ss]; k++) {
               const int c = P->bc.vfield[dd][ss][k];
-              if (c >= L.dof) continue;
+              if (c >= L.dof || fs.vcount >= kMaxDof) continue;
               fs.vfield[fs.vcount] = c; fs.vvalue[fs.vcount] = P->bc.vvalue[dd][ss][k]; fs.vcount++;
             }
           }

@@ -37,12 +37,13 @@ int nccl_fail(ncclResult_t r, const char* what) {
   } while (0)
 
 // values[rowbase[row]*bs2 + e] += recv[off[t] + e] for the t-th listed row; one warp per row
+// off[t]: block offset of the t-th listed row inside its peer's slab (prefix sum built once at plan creation)
 __global__ void add_rows_kernel(const int* __restrict__ rows, const int64_t* __restrict__ off, int nrows, const int64_t* __restrict__ rowbase,
                                 int bs2, double* __restrict__ values, const double* __restrict__ recv) {
   const int wpb = blockDim.x / 32, lane = threadIdx.x & 31;
   for (int t = blockIdx.x * wpb + threadIdx.x / 32; t < nrows; t += gridDim.x * wpb) {
     const int row = rows[t];
-    const int64_t b0 = rowbase[row] * bs2, n = (rowbase[row + 1] - rowbase[row]) * bs2, o = off[t];
+    const int64_t b0 = rowbase[row] * bs2, n = (rowbase[row + 1] - rowbase[row]) * bs2, o = off[t] * bs2;
     for (int64_t e = lane; e < n; e += 32) values[b0 + e] += recv[o + e];
   }
 }
@@ -105,35 +106,31 @@ int exchange_ghost_rows(petiga_cuda_plan* P, int block, double* values, double* 
   for (size_t i = 0; i < L.recv.size(); i++) { moff[i] = total; if (mat) total += (size_t)L.recv[i].nblocks * bs2; }
   for (size_t i = 0; i < L.recv.size(); i++) { voff[i] = total; if (vec) total += L.recv[i].rows.size() * dof; }
   if ((rc = ensure_recv(P, total))) return rc;
-  PC_NCCL(g_nccl.GroupStart());
+  // a failed Send/Recv must not leave the NCCL group open: close it, then report
+  ncclResult_t gr = g_nccl.GroupStart();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclGroupStart");
+  auto post = [&](ncclResult_t r) { if (gr == ncclSuccess && r != ncclSuccess) gr = r; };
   for (const auto& s : L.send) {
-    if (mat) PC_NCCL(g_nccl.Send(P->d_ghost_values + (size_t)(s.first_block - L.nnz_own) * bs2, (size_t)s.nblocks * bs2, ncclDouble, s.rank, comm, P->stream));
-    if (vec) PC_NCCL(g_nccl.Send(P->d_rhs_loc + (size_t)s.first_row * dof, (size_t)s.nrows * dof, ncclDouble, s.rank, comm, P->stream));
+    if (mat) post(g_nccl.Send(P->d_ghost_values + (size_t)(s.first_block - L.nnz_own) * bs2, (size_t)s.nblocks * bs2, ncclDouble, s.rank, comm, P->stream));
+    if (vec) post(g_nccl.Send(P->d_rhs_loc + (size_t)s.first_row * dof, (size_t)s.nrows * dof, ncclDouble, s.rank, comm, P->stream));
   }
   for (size_t i = 0; i < L.recv.size(); i++) {
     const auto& r = L.recv[i];
-    if (mat) PC_NCCL(g_nccl.Recv(P->d_recv + moff[i], (size_t)r.nblocks * bs2, ncclDouble, r.rank, comm, P->stream));
-    if (vec) PC_NCCL(g_nccl.Recv(P->d_recv + voff[i], r.rows.size() * dof, ncclDouble, r.rank, comm, P->stream));
+    if (mat) post(g_nccl.Recv(P->d_recv + moff[i], (size_t)r.nblocks * bs2, ncclDouble, r.rank, comm, P->stream));
+    if (vec) post(g_nccl.Recv(P->d_recv + voff[i], r.rows.size() * dof, ncclDouble, r.rank, comm, P->stream));
   }
-  PC_NCCL(g_nccl.GroupEnd());
+  ncclResult_t ge = g_nccl.GroupEnd();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclSend/ncclRecv (ghost rows)");
+  if (ge != ncclSuccess) return nccl_fail(ge, "ncclGroupEnd");
   P->launches += 1;
   for (size_t i = 0; i < L.recv.size(); i++) {
     const auto& r = L.recv[i];
     const int n = (int)r.rows.size();
     const int* rows = P->d_recv_rows + P->recv_row_off[i];
-    if (mat) {
-      // per-row staging offsets are a prefix sum over the listed rows; build once per peer and cache on the device
-      static thread_local std::vector<int64_t> tmp;
-      tmp.resize(n);
-      int64_t o = (int64_t)moff[i];
-      for (int t = 0; t < n; t++) { tmp[t] = o; o += (L.rowbase[r.rows[t] + 1] - L.rowbase[r.rows[t]]) * bs2; }
-      int64_t* d_off = nullptr;
-      PC_CUDA(cudaMallocAsync((void**)&d_off, (size_t)n * sizeof(int64_t), P->stream));
-      PC_CUDA(cudaMemcpyAsync(d_off, tmp.data(), (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, P->stream));
-      PC_CUDA(cudaStreamSynchronize(P->stream));   // tmp is reused; exchange is once per assembly
-      add_rows_kernel<<<std::max(1, std::min((n + 7) / 8, P->num_sms * 8)), 256, 0, P->stream>>>(rows, d_off, n, P->d_rowbase, bs2, values, P->d_recv);
+    if (mat) {   // per-row offsets inside the slab were uploaded once by petiga_cuda_plan_create: no host work, no sync here
+      add_rows_kernel<<<std::max(1, std::min((n + 7) / 8, P->num_sms * 8)), 256, 0, P->stream>>>(rows, P->d_recv_off + P->recv_row_off[i], n, P->d_rowbase, bs2,
+                                                                                               values, P->d_recv + moff[i]);
       PC_CUDA(cudaGetLastError());
-      PC_CUDA(cudaFreeAsync(d_off, P->stream));
       P->launches++;
     }
     if (vec) {
@@ -164,12 +161,15 @@ int halo_state(petiga_cuda_plan* P, const double* U_own, double* U_loc) {
     PC_CUDA(cudaGetLastError());
     P->launches++;
   }
-  PC_NCCL(g_nccl.GroupStart());
-  for (size_t i = 0; i < L.recv.size(); i++)
-    PC_NCCL(g_nccl.Send(P->d_recv + off[i], L.recv[i].rows.size() * dof, ncclDouble, L.recv[i].rank, comm, P->stream));
-  for (const auto& s : L.send)
-    PC_NCCL(g_nccl.Recv(U_loc + (size_t)s.first_row * dof, (size_t)s.nrows * dof, ncclDouble, s.rank, comm, P->stream));
-  PC_NCCL(g_nccl.GroupEnd());
+  ncclResult_t gr = g_nccl.GroupStart();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclGroupStart");
+  for (size_t i = 0; i < L.recv.size() && gr == ncclSuccess; i++)
+    gr = g_nccl.Send(P->d_recv + off[i], L.recv[i].rows.size() * dof, ncclDouble, L.recv[i].rank, comm, P->stream);
+  for (size_t i = 0; i < L.send.size() && gr == ncclSuccess; i++)
+    gr = g_nccl.Recv(U_loc + (size_t)L.send[i].first_row * dof, (size_t)L.send[i].nrows * dof, ncclDouble, L.send[i].rank, comm, P->stream);
+  ncclResult_t ge = g_nccl.GroupEnd();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclSend/ncclRecv (state halo)");
+  if (ge != ncclSuccess) return nccl_fail(ge, "ncclGroupEnd");
   P->launches++;
   return 0;
 }

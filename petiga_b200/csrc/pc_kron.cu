@@ -750,12 +750,12 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
         FixSide& fs = kp.bc[d][s];
         for (int k = 0; k < P->bc.vcount[d][s]; k++) {
           int c = P->bc.vfield[d][s][k];
-          if (c >= L.dof) continue;
+          if (c >= L.dof || fs.vcount >= kMaxDof) continue;
           fs.vfield[fs.vcount] = c; fs.vvalue[fs.vcount] = P->bc.vvalue[d][s][k]; fs.vcount++;
         }
         for (int k = 0; k < P->bc.lcount[d][s]; k++) {
           int c = P->bc.lfield[d][s][k];
-          if (c >= L.dof) continue;
+          if (c >= L.dof || fs.lcount >= kMaxDof) continue;
           fs.lfield[fs.lcount] = c; fs.lvalue[fs.lcount] = P->bc.lvalue[d][s][k]; fs.lcount++;
         }
         if (!L.ax[d].periodic && (fs.vcount || fs.lcount)) kp.any_bc = 1;

@@ -57,6 +57,7 @@ struct petiga_cuda_plan {
   double* d_V_loc = nullptr;
   double* d_recv = nullptr; size_t recv_cap = 0;
   int* d_recv_rows = nullptr;      // concatenated recv row lists
+  int64_t* d_recv_off = nullptr;   // same indexing: block offset of each listed row inside its peer's slab
   std::vector<size_t> recv_row_off;
   // host staging for *_host entry points
   double* h_pinned = nullptr; size_t h_pinned_cap = 0;

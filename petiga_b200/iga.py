@@ -84,9 +84,17 @@ def iga_partition(size, rank, dim, N):
     return list(n)[:dim], list(i)[:dim]
 
 
+def _vp(handle):
+    """Handles cross ctypes as c_void_p objects: a bare Python int is converted to a 32-bit C int and would truncate a
+    64-bit pointer (it only worked while malloc returned addresses below 4 GB)."""
+    if isinstance(handle, C.c_void_p):
+        return handle
+    return C.c_void_p(handle)
+
+
 class Vec:
     def __init__(self, iga, handle):
-        self.iga, self.h = iga, handle
+        self.iga, self.h = iga, _vp(handle)
 
     @property
     def size(self):
@@ -111,14 +119,13 @@ class Vec:
 
     def destroy(self):
         if self.h:
-            h = C.c_void_p(self.h)
-            load_host().VecDestroy(C.byref(h))
-            self.h = None
+            load_host().VecDestroy(C.byref(self.h))
+            self.h = C.c_void_p()
 
 
 class Mat:
     def __init__(self, iga, handle):
-        self.iga, self.h = iga, handle
+        self.iga, self.h = iga, _vp(handle)
         n, nnz, bs, baij = C.c_int(), C.c_int64(), C.c_int(), C.c_int()
         _chk(load_host().MatGetSizesIGA(self.h, C.byref(n), C.byref(nnz), C.byref(bs), C.byref(baij)))
         self.nrows_scalar, self.nnz, self.bs, self.baij = n.value, nnz.value, bs.value, bool(baij.value)
@@ -147,9 +154,8 @@ class Mat:
 
     def destroy(self):
         if self.h:
-            h = C.c_void_p(self.h)
-            load_host().MatDestroy(C.byref(h))
-            self.h = None
+            load_host().MatDestroy(C.byref(self.h))
+            self.h = C.c_void_p()
 
 
 class IGA:
@@ -280,33 +286,33 @@ class IGA:
     def CreateMat(self):
         m = C.c_void_p()
         _chk(self.H.IGACreateMat(self.h, C.byref(m)))
-        return Mat(self, m.value)
+        return Mat(self, m)
 
     def CreateVec(self):
         v = C.c_void_p()
         _chk(self.H.IGACreateVec(self.h, C.byref(v)))
-        return Vec(self, v.value)
+        return Vec(self, v)
 
     def ComputeVector(self, B):
-        _chk(self.H.IGAComputeVector(self.h, C.c_void_p(B.h)))
+        _chk(self.H.IGAComputeVector(self.h, B.h))
 
     def ComputeMatrix(self, A):
-        _chk(self.H.IGAComputeMatrix(self.h, C.c_void_p(A.h)))
+        _chk(self.H.IGAComputeMatrix(self.h, A.h))
 
     def ComputeSystem(self, A, B):
-        _chk(self.H.IGAComputeSystem(self.h, C.c_void_p(A.h), C.c_void_p(B.h)))
+        _chk(self.H.IGAComputeSystem(self.h, A.h, B.h))
 
     def ComputeFunction(self, U, F):
-        _chk(self.H.IGAComputeFunction(self.h, C.c_void_p(U.h), C.c_void_p(F.h)))
+        _chk(self.H.IGAComputeFunction(self.h, U.h, F.h))
 
     def ComputeJacobian(self, U, J):
-        _chk(self.H.IGAComputeJacobian(self.h, C.c_void_p(U.h), C.c_void_p(J.h)))
+        _chk(self.H.IGAComputeJacobian(self.h, U.h, J.h))
 
     def ComputeIFunction(self, a, V, t, U, F):
-        _chk(self.H.IGAComputeIFunction(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(F.h)))
+        _chk(self.H.IGAComputeIFunction(self.h, C.c_double(a), V.h, C.c_double(t), U.h, F.h))
 
     def ComputeIJacobian(self, a, V, t, U, J):
-        _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), C.c_void_p(V.h), C.c_double(t), C.c_void_p(U.h), C.c_void_p(J.h)))
+        _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), V.h, C.c_double(t), U.h, J.h))
 
     def GetOwnedNaturalIndices(self):
         inf = self.info()
@@ -329,10 +335,10 @@ class IGA:
         _chk(self.H.IGAWrite(self.h, filename.encode()))
 
     def ReadVec(self, vec, filename):
-        _chk(self.H.IGAReadVec(self.h, C.c_void_p(vec.h), filename.encode()))
+        _chk(self.H.IGAReadVec(self.h, vec.h, filename.encode()))
 
     def WriteVec(self, vec, filename):
-        _chk(self.H.IGAWriteVec(self.h, C.c_void_p(vec.h), filename.encode()))
+        _chk(self.H.IGAWriteVec(self.h, vec.h, filename.encode()))
 
     def GetGeometryArrays(self):
         sizes, nsd, rat = (C.c_int * 3)(), C.c_int(), C.c_int()
@@ -349,7 +355,7 @@ class IGA:
         fn = C.cast(getattr(self.H, "IGADeviceScalar_" + scalar), C.c_void_p)
         S = (C.c_double * n)()
         cx = (C.c_double * max(1, len(ctx)))(*ctx)
-        _chk(self.H.IGAComputeScalar(self.h, C.c_void_p(U.h if U is not None else None), n, S, fn, C.cast(cx, C.c_void_p)))
+        _chk(self.H.IGAComputeScalar(self.h, (U.h if U is not None else None), n, S, fn, C.cast(cx, C.c_void_p)))
         return np.array(list(S))
 
     def ComputeErrorNorm(self, k, U=None, exact=None, ctx=()):
@@ -357,7 +363,7 @@ class IGA:
         fn = C.cast(getattr(self.H, "IGADeviceExact_" + exact), C.c_void_p) if exact else C.c_void_p(None)
         out = (C.c_double * self.dof)()
         cx = (C.c_double * max(1, len(ctx)))(*ctx)
-        _chk(self.H.IGAComputeErrorNorm(self.h, k, C.c_void_p(U.h if U is not None else None), fn, out, C.cast(cx, C.c_void_p)))
+        _chk(self.H.IGAComputeErrorNorm(self.h, k, (U.h if U is not None else None), fn, out, C.cast(cx, C.c_void_p)))
         return np.array(list(out))
 
     # ---- introspection ----

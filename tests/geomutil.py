@@ -2,27 +2,7 @@
 import numpy as np
 
 
-def greville(U, p):
-    U = np.asarray(U)
-    n = len(U) - p - 1
-    return np.array([U[i + 1:i + p + 1].sum() / p for i in range(n)])
-
-
-def uniform_knots(p, N, C=None, lo=0.0, hi=1.0):
-    C = p - 1 if C is None else C
-    s = p - C
-    inner = np.repeat(lo + np.arange(1, N) / N * (hi - lo), s)
-    return np.concatenate([[lo] * (p + 1), inner, [hi] * (p + 1)])
-
-
-def perturbed_identity(dim, p, N, amp=0.05):
-    """SURVEY 8d cfg 2g: control points = Greville abscissae + amp*prod sin(2 pi x_d) per component, W = 1.
-    Returns X[natural (k,j,i)][dim]."""
-    N = [N] * dim if np.isscalar(N) else N
-    g = [greville(uniform_knots(p, N[d]), p) for d in range(dim)]
-    grids = np.meshgrid(*g[::-1], indexing="ij")[::-1]   # grids[d] indexed [k][j][i]
-    bump = amp * np.prod([np.sin(2 * np.pi * x) for x in grids], axis=0)
-    return np.stack([grids[d] + bump for d in range(dim)], axis=-1)
+from petiga_b200.cases import greville, uniform_knots, perturbed_identity  # noqa: F401
 
 
 def _insert_knot_1d(U, p, Pw, u):

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from tests.common import Case, state_vectors
+from petiga_b200.cases import Case, state_vectors
 
 FP64_TF = 37.2
 
