@@ -84,54 +84,14 @@ def build_case(mesh, p=3, geometry=None):
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, threads=None, per_rank=None, native=True):
-    """Oracle ("port") timed on host cores: T processes = T emulated MPI ranks of the reference's box partition,
-    each integrating its own element box of a bounded sample mesh (per_rank^3 elements per rank)."""
-    import multiprocessing as mp
-    from oracle.oracle import partition
-    T = threads or os.cpu_count() or 1
-    T = max(1, T)
-    per_rank = per_rank or 12
-    grid, _ = partition(T, 0, 3, [per_rank * T] * 3)     # reference's own processor grid for T ranks
-    mesh = [per_rank * g for g in grid]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(T, initializer=_cpu_worker_init, initargs=(mesh, T, native)) as pool:
-        times = []
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker_step, range(T))
-            dt = time.perf_counter() - t0
-            if it >= warmup:
-                times.append(dt)
-    nel = mesh[0] * mesh[1] * mesh[2]
-    sec = sum(times) / len(times)
-    el_s = nel / sec
-    return dict(seconds=sec, elements=nel, elements_per_s=el_s, mnnz_per_s=el_s * NNZ_FULL / NEL_FULL / 1e6, cores=T, mesh=mesh,
-                sample="Poisson3D p=3 C2 on a %dx%dx%d sub-mesh (%d^3 elements per emulated rank, %d ranks as processes, "
-                       "reference box partition), one IGAComputeSystem element loop per step; Mnnz/s = elements/s x "
-                       "(741217625 nnz / 2097152 elements of the full 128^3 mesh)" % (mesh[0], mesh[1], mesh[2], per_rank, T))
-
-
-_W = {}
-
-
-def _cpu_worker_init(mesh, T, native):
-    import numpy as np
-    from oracle.oracle import OracleIGA
-    o = OracleIGA(3, 1, native=native)
-    for d in range(3):
-        o.axis_uniform(d, 3, mesh[d])
-        for s in range(2):
-            o.boundary_value(d, s, 0, 1.0)
-    rp, ci, _ = o.pattern(T)
-    _W.update(o=o, T=T, vals=np.zeros((len(ci), 1, 1)), rhs=np.zeros((len(rp) - 1, 1)))
-
-
-def _cpu_worker_step(rank):
-    _W["vals"][:] = 0
-    _W["rhs"][:] = 0
-    _W["o"].assemble_rank("SYSTEM", "POISSON", [], _W["T"], rank, _W["vals"], _W["rhs"])
-    return 0
+def cpu_reference_run(steps, warmup, threads=None, per_rank=12):
+    """The reference's CPU assembly algorithm on the host cores (oracle/cpu_reference.py; the only place this file executes
+    oracle/): T emulated MPI ranks on T threads, reference box partition, ghost rows through a stash + assembly-end sum,
+    library rebuilt with -march=native on this box."""
+    from oracle.cpu_reference import run_cfg2_sample
+    r = run_cfg2_sample(steps, warmup, T=threads, per_rank=per_rank, native=True)
+    r["mnnz_per_s"] = r["elements_per_s"] * NNZ_FULL / NEL_FULL / 1e6
+    return r
 
 
 def main_reference(args):
@@ -144,7 +104,8 @@ def main_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "elements_per_s": r["elements_per_s"],
         "config": {"workload": "demo/Poisson3D p=3 C2 128^3 dof=1 AIJ IGAComputeSystem (CPU sample, see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "cpu_model": r["cpu_model"], "ghost_row_sum": True, "stash_entries_per_step": r["stash_entries"]},
         "e2e": {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,6 +148,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-quad", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity cases run before the timed region")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations (N=1 only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -220,6 +183,32 @@ def main():
         assert L.petiga_cuda_comm_init(C.byref(comm), world, rank, raw, local) == 0, L.petiga_cuda_last_error()
         nccl = comm.value
 
+    # -------- parity on the live communicator, before anything is timed: small cases against committed golden vectors
+    #          (CPU-oracle outputs in natural numbering, tests/golden/multirank_cases.npz; no oracle code runs here) --------
+    parity = None
+    if not args.no_parity:
+        from petiga_b200.parity import check_cases
+
+        def _allgather(a):
+            if world == 1:
+                return [a]
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([t.numel()], dtype=torch.int64, device="cuda"))
+            mx = int(max(int(x.item()) for x in sizes))
+            pad = torch.zeros(mx, dtype=t.dtype, device="cuda"); pad[:t.numel()] = t
+            outs = [torch.zeros(mx, dtype=t.dtype, device="cuda") for _ in range(world)]
+            dist.all_gather(outs, pad)
+            return [o[:int(n.item())].cpu().numpy() for o, n in zip(outs, sizes)]
+
+        def _allreduce(a):
+            if world == 1:
+                return a
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+        parity = check_cases(rank, world, nccl, local, _allgather, _allreduce)
+
     stream = torch.cuda.Stream()
     case = build_case(args.mesh, geometry=args.geometry)
     g = case.product(rank=rank, size=world, nccl=nccl, device=local, setup=False)
@@ -229,7 +218,7 @@ def main():
     g.SetOption("quad_impl", args.quad_impl)
     g.SetForm("SYSTEM", "POISSON")
     A, B = g.CreateMat(), g.CreateVec()          # IGACreateMat: pattern built once, outside the timed region
-    nnz_local = A.nnz
+    nnz_local, nvec_local = A.nnz, B.size
     nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(nnz_t)
@@ -334,6 +323,14 @@ def main():
                "h2d_bytes_per_step": C.sizeof(bc), "d2h_bytes_per_step": (nval + nvec) * 8, "steps": ksteps, "rhs_checksum8": chk}
         L.petiga_cuda_host_free(hv); L.petiga_cuda_host_free(hr)
 
+    # -------- the other BASELINE configurations, one GPU, device-resident (secondary rows of SURVEY 8d) --------
+    configs = None
+    if world == 1 and not args.no_configs and args.mesh == 128 and args.geometry == "identity":
+        A.destroy(); B.destroy(); g.Destroy()
+        A = B = g = None
+        torch.cuda.empty_cache()
+        configs = sweep_configs(stream, measured_peaks())
+
     if rank != 0:
         return 0
     peaks = measured_peaks()
@@ -348,7 +345,7 @@ def main():
     sec = ms * 1e-3
     value = nnz_global / sec / 1e6
     if path_used == 2:     # separable path: one write-once kernel per step, HBM bound
-        alg_bytes = 8.0 * (nnz_local + B.size)
+        alg_bytes = 8.0 * (nnz_local + nvec_local)
         # launch duration = CUDA-event time of the timed region / K (each step is exactly one launch of this kernel; the
         # inter-launch gaps are inside, so this is the conservative figure); kernel_ms_sync = the plan's own per-launch events
         roof = {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
@@ -391,12 +388,120 @@ def main():
                                                         "FP64 operations than W_e, so frac can exceed 1"}}
     if e2e:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"] = parity
+    if configs is not None:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(1, 1, threads=1, per_rank=16)
-        line["cpu_baseline"] = {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": 1, "kind": "port", "sample": r["sample"],
-                                "elements_per_s": r["elements_per_s"]}
+        # the reference's CPU algorithm on ALL host cores (a bounded sample of the same workload: ~10-20 s of CPU work), with the
+        # ghost-row sum; cfg 1 at its full size on one core beside it (BASELINE.json configs[0] is the CPU-runnable case)
+        r = cpu_reference_run(2, 1, threads=args.cpu_threads, per_rank=12)
+        line["cpu_baseline"] = {"value": r["mnnz_per_s"], "unit": "Mnnz/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                "elements_per_s": r["elements_per_s"], "cpu_model": r["cpu_model"], "ghost_row_sum": True}
+        try:
+            from oracle.cpu_reference import run_cfg1_full
+            c1 = run_cfg1_full()
+            line["cpu_baseline"]["cfg1_full_size_1core"] = {"value": c1["mnnz_per_s"], "unit": "Mnnz/s", "ms": c1["seconds"] * 1e3,
+                                                             "elements_per_s": c1["elements_per_s"]}
+        except Exception as e:      # the headline must not die on the side figure
+            line["cpu_baseline"]["cfg1_full_size_1core"] = {"error": str(e)}
     _emit(line)
     return 0
+
+
+def sweep_configs(stream, peaks):
+    """cfg 1, 2g, 3, 4, 5 of BASELINE.json on one GPU: per config the path and kernel that ran, CUDA-event ms per call,
+    Mnnz/s, elements/s and the roofline fraction of its bound (HBM for the write-once path: 8 B per stored value; FP64 for
+    the quadrature kernels: the flops the kernel EXECUTES, reported by the library, over the measured DFMA peak)."""
+    import numpy as np
+    import torch
+    import petiga_b200 as pb
+    from petiga_b200.cases import baseline_config, state_vectors
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic = {}
+    out = []
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    for name, steps in (("cfg1", 20), ("cfg2g", 3), ("cfg3", 5), ("cfg4", 5), ("cfg5", 20), ("cfg5f", 20)):
+        case, slot, form, prm, w_e, state = baseline_config(name)
+        g = case.product(setup=False)
+        g.SetStream(stream.cuda_stream)
+        g.SetUp()
+        g.SetForm(slot, form, prm)
+        A = g.CreateMat() if slot in ("SYSTEM", "IJACOBIAN") else None
+        B = g.CreateVec() if slot in ("SYSTEM", "IFUNCTION") else None
+        U = V = None
+        if state:
+            t = g.CreateVec(); n = t.size; t.destroy()
+            u, v = state_vectors(n)
+            U, V = g.CreateVec(), g.CreateVec()
+            U.set(u); V.set(v)
+
+        def call():
+            if slot == "SYSTEM": g.ComputeSystem(A, B)
+            elif slot == "IJACOBIAN": g.ComputeIJacobian(1.0e3, V, 0.0, U, A)
+            else: g.ComputeIFunction(1.0e3, V, 0.0, U, B)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            g.SetOption("async", 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = g.GetStat("launches")
+            e0.record(stream)
+            for _ in range(steps):
+                call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            g.SetOption("async", 0)
+        ms = e0.elapsed_time(e1) / steps
+        nel = int(np.prod(g.info()["nel"]))
+        nnz = (A.nnz * (case.dof ** 2 if A.baij else 1)) if A is not None else 0
+        nvec = B.size if B is not None else 0
+        path = {1: "quadrature", 2: "kronecker"}.get(int(g.GetStat("last_path")), "?")
+        row = {"config": name, "workload": WORKLOADS[name], "path": path, "kernel": kernel_name(g, path), "ms_per_call": ms, "steps": steps,
+               "launches_per_call": (g.GetStat("launches") - l0) / steps, "elements": nel, "nnz": nnz,
+               "elements_per_s": nel / (ms * 1e-3), "value": (nnz / (ms * 1e-3) / 1e6) if nnz else None, "unit": "Mnnz/s"}
+        bytes_alg = 8.0 * (nnz + nvec * (1 + (2 if state else 0))) + (8.0 * 3 * g.info()["nnp"][0] * g.info()["nnp"][1] * g.info()["nnp"][2] if case.geometry else 0.0)
+        hb = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "algorithmic_bytes": bytes_alg}
+        hb["frac"] = hb["achieved"] / hb["peak"]
+        if path == "kronecker" and form != "L2PROJECTION":
+            row["roofline"] = hb
+        else:
+            fl = g.GetStat("last_flops")
+            fp = {"bound": "fp64", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks.get("fp64_tflops_measured", 34.1), "unit": "TFLOP/s",
+                  "executed_flop_per_call": fl, "algorithmic_flop_W_e": float(w_e) * nel,
+                  "note": "achieved counts the FP64 operations the kernel executes (library stat last_flops), not SURVEY 8(d)'s W_e"}
+            fp["frac"] = fp["achieved"] / fp["peak"]
+            row["roofline"] = fp
+            row["roofline_hbm"] = hb
+        key = "%s/%s" % (name, path)
+        row["traffic"] = traffic.get(key, {}).get("dram_bytes_per_launch")
+        out.append(row)
+        for x in (A, B, U, V):
+            if x is not None:
+                x.destroy()
+        g.Destroy()
+        torch.cuda.empty_cache()
+    return out
+
+
+WORKLOADS = {
+    "cfg1": "demo/Poisson2D p=2 C1 64x64 dof=1 AIJ IGAComputeSystem",
+    "cfg2": "demo/Poisson3D p=3 C2 128^3 dof=1 AIJ IGAComputeSystem",
+    "cfg2g": "demo/Poisson3D p=3 C2 128^3 on a mapped geometry (Greville + 0.05 sin sin sin), IGAComputeSystem",
+    "cfg3": "demo/L2Projection 3-D p=4 C3 64^3 dof=1 AIJ IGAComputeSystem (-function linear)",
+    "cfg4": "demo/Elasticity3D p=2 C1 96^3 dof=3 BAIJ IGAComputeSystem",
+    "cfg5": "demo/CahnHilliard2D p=2 C1 512^2 periodic IGAComputeIJacobian (shift 1e3, seed 20261017 state)",
+    "cfg5f": "demo/CahnHilliard2D p=2 C1 512^2 periodic IGAComputeIFunction",
+}
+
+
+def kernel_name(g, path):
+    if path == "kronecker":
+        return "kron_rows_kernel"
+    return {0: "quad_sf_kernel", 1: "quad_kernel", 2: "quad_gen_kernel", 3: "quad_sf3_kernel"}.get(int(g.GetStat("last_impl")), "?")
 
 
 def _bc_struct(case):

@@ -201,6 +201,9 @@ int petiga_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int petiga_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int petiga_cuda_host_alloc(void **ptr, size_t bytes);   /* pinned */
 int petiga_cuda_host_free(void *ptr);
+/* sum (a-b)^2 and sum b^2 over n device doubles on the current device (deterministic; synchronous): lets a caller compare two
+   assembled value arrays (e.g. the two assembly paths at full size) without copying 2 x 5.9 GB to the host */
+int petiga_cuda_diff_norm2(const double *d_a, const double *d_b, size_t n, double *diff2, double *ref2);
 
 /* ---- NCCL bootstrap (one rank per GPU; the id travels over the caller's own channel, e.g. MPI_Bcast
         in PetIGA or torch.distributed in the test harness) ---- */

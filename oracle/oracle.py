@@ -12,9 +12,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6)
+SLOT = dict(VECTOR=0, MATRIX=1, SYSTEM=2, FUNCTION=3, JACOBIAN=4, IFUNCTION=5, IJACOBIAN=6,
+            IEFUNCTION=7, IEJACOBIAN=8, RHSFUNCTION=9, RHSJACOBIAN=10, I2FUNCTION=11, I2JACOBIAN=12)
+MAT_SLOTS = ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN", "IEJACOBIAN", "RHSJACOBIAN", "I2JACOBIAN")
+VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION", "IEFUNCTION", "RHSFUNCTION", "I2FUNCTION")
 FORM = dict(POISSON=0, LAPLACE=1, L2PROJECTION=2, ELASTICITY3D=3, ELASTICITY=4, CAHNHILLIARD2D=5, BRATU=6, MASS=7,
-            BOUNDARYINTEGRAL=8, NEUMANN=9, CAHNHILLIARD3D=10, CONVTEST=11)
+            BOUNDARYINTEGRAL=8, NEUMANN=9, CAHNHILLIARD3D=10, CONVTEST=11, SNES2D=12, PATTERNFORMATION=13, ELASTICROD=14, NITSCHE=15)
 SCALAR = dict(ERRNORM=0, CH_STATS=1)
 
 _dp = C.POINTER(C.c_double)
@@ -97,6 +100,7 @@ def lib(native=False):
     L.oiga_set_fixtable.argtypes = [C.c_void_p, _dp, C.c_long]
     L.oiga_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.oiga_get_info.argtypes = [C.c_void_p, _ip]
+    L.oiga_set_aux.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp]
     for name, rt in [("oiga_knots", _dp), ("oiga_spans", _ip), ("oiga_basis_offset", _ip), ("oiga_basis_detJac", _dp),
                      ("oiga_basis_weight", _dp), ("oiga_basis_point", _dp), ("oiga_basis_value", _dp)]:
         getattr(L, name).restype = rt
@@ -117,6 +121,15 @@ def lib(native=False):
                                 C.c_void_p, _dp, _dp]
     L.oiga_assemble_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
                                      C.c_void_p, _dp, _dp]
+    L.oiga_assemble_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
+                                      C.c_void_p, _dp, _dp]
+    L.oiga_stash_create.restype = C.c_void_p
+    L.oiga_stash_destroy.argtypes = [C.c_void_p]
+    L.oiga_stash_count.restype = C.c_long
+    L.oiga_stash_count.argtypes = [C.c_void_p]
+    L.oiga_assemble_rank_stash.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp,
+                                           C.c_void_p, _dp, _dp, C.c_void_p]
+    L.oiga_stash_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _dp, _dp]
     L.oiga_compute_scalar.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
     L.oiga_tabulate_element.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 12
     if not native:
@@ -249,19 +262,22 @@ class OracleIGA:
                                        self._pat[size], _d(vals), _d(rhs))
         assert rc == 0, rc
 
-    def assemble(self, slot, form, params=(), size=1, shift=0.0, V=None, t=0.0, U=None):
-        """Returns (values[nnzb, dof, dof] or None, rhs[nrows, dof] or None) of one full assembly."""
+    def assemble(self, slot, form, params=(), size=1, shift=0.0, V=None, t=0.0, U=None, W=None, shift2=0.0, t0=0.0):
+        """Returns (values[nnzb, dof, dof] or None, rhs[nrows, dof] or None) of one full assembly.
+        W, shift2, t0: third vector / second shift / second time of the IE (U0, t0) and I2 (A, shiftV) drivers."""
         rp, ci, _ = self.pattern(size)
         p = self._pat[size]
         n, nnz, dof = len(rp) - 1, len(ci), self.dof
         slot_i = SLOT[slot]
-        want_mat = slot in ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN")
-        want_vec = slot in ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION")
+        want_mat = slot in MAT_SLOTS
+        want_vec = slot in VEC_SLOTS
         vals = np.zeros((nnz, dof, dof)) if want_mat else None
         rhs = np.zeros((n, dof)) if want_vec else None
         prm = np.ascontiguousarray(list(params) + [0.0] * 4, dtype=np.float64)
         Uc = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
         Vc = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+        Wc = None if W is None else np.ascontiguousarray(W, dtype=np.float64)
+        self.L.oiga_set_aux(self.h, shift2, t0, _d(Wc))
         rc = self.L.oiga_assemble(self.h, size, slot_i, FORM[form], _d(prm), shift, _d(Vc), t, _d(Uc), p, _d(vals), _d(rhs))
         assert rc == 0, "oracle assemble failed rc=%d" % rc
         return vals, rhs

@@ -71,11 +71,15 @@ typedef struct {
   int *lgmap;              /* ghost node -> global (PETSc) node */
   double *geometryX, *rationalW, *fixtableU;
   int tables_ready;
+  /* third state vector / second shift / second time of the IE and I2 drivers (set by oiga_set_aux before oiga_assemble) */
+  double aux_shift2, aux_t0; const double *aux_W;
 } OIGA;
 
-enum { SLOT_VECTOR=0, SLOT_MATRIX, SLOT_SYSTEM, SLOT_FUNCTION, SLOT_JACOBIAN, SLOT_IFUNCTION, SLOT_IJACOBIAN };
+enum { SLOT_VECTOR=0, SLOT_MATRIX, SLOT_SYSTEM, SLOT_FUNCTION, SLOT_JACOBIAN, SLOT_IFUNCTION, SLOT_IJACOBIAN,
+       SLOT_IEFUNCTION, SLOT_IEJACOBIAN, SLOT_RHSFUNCTION, SLOT_RHSJACOBIAN, SLOT_I2FUNCTION, SLOT_I2JACOBIAN };   /* src/petigats.c:182-477, src/petigats2.c:23-175 */
 enum { FORM_POISSON=0, FORM_LAPLACE, FORM_L2PROJECTION, FORM_ELASTICITY3D, FORM_ELASTICITY,
-       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN, FORM_CAHNHILLIARD3D, FORM_CONVTEST };
+       FORM_CAHNHILLIARD2D, FORM_BRATU, FORM_MASS, FORM_BOUNDARYINTEGRAL, FORM_NEUMANN, FORM_CAHNHILLIARD3D, FORM_CONVTEST,
+       FORM_SNES2D, FORM_PATTERNFORMATION, FORM_ELASTICROD, FORM_NITSCHE };
 
 /* ------------------------------------------------------------------------------------------ */
 /* axis: src/petigaaxis.c                                                                     */
@@ -743,6 +747,11 @@ static void elem_tabulate(Elem *e)
       for (i = 0; i < dim; i++) { e->mapX[1][q*nsd*dim + i*(dim+1)] = 1.0; e->mapU[1][q*dim*nsd + i*(dim+1)] = 1.0; }
     }
     for (k = 0; k <= ord; k++) memcpy(e->shape[k], e->basis[k], sizeof(double)*(size_t)nqp*nen*ipow(dim,k));
+    if (bnd) for (q = 0; q < nqp; q++) {   /* petigaelem.c:1018-1021: unit normal of the parametric face, detS = 1 */
+      double *n = e->normal + (size_t)q*nsd;
+      for (i = 0; i < nsd; i++) n[i] = 0.0;
+      e->detS[q] = 1.0; n[bax] = bsd ? 1.0 : -1.0;
+    }
     return;
   }
   /* GeometryMap: src/petigamapgeo.f90.in:3-71.  X_k(:,i) += X(i,node)*M_k(:,node); C layout mapX[k][q][i][dim^k] */
@@ -960,6 +969,9 @@ typedef struct { /* what a callback reads from IGAPoint: include/petiga.h:644-70
   const double *N0, *N1, *N2;  /* shape[0..2] of this point */
   const double *x;             /* mapX[0] (or mapU[0] when no geometry) */
   int atboundary, boundary_id; const double *normal;   /* petiga.h:645-647,668 */
+  const double *E1;            /* mapU[1] of this point ([dim][nsd]) or NULL without geometry (IGAPointFormInvGradGeomMap) */
+  double L[3];                 /* IGAPointFormScale: detJac of the element per axis (petigapoint.c:209-223) */
+  int maxdeg;                  /* max_i axis[i]->p (demo/NitscheMethod.c Degree()) */
 } Point;
 
 static double l2_function(int choice, int dim, const double x[3]) /* demo/L2Projection.c:3-61 */
@@ -1057,6 +1069,31 @@ static int form_system(int form, const double *prm, const Point *p, double *K, d
     for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i];
       K[a*nen+b] = c*p->N0[a]*p->N0[b] + k*sum; } F[a] = p->N0[a]*f; }
     return 0; }
+  case FORM_NITSCHE: { /* demo/NitscheMethod.c:70-119: Poisson with f = -2 dim inside; Nitsche terms on the visited faces */
+    if (!p->atboundary) {
+      double f = -2.0*dim;
+      for (a = 0; a < nen; a++) { for (b = 0; b < nen; b++) { double sum = 0.0; for (i = 0; i < dim; i++) sum += p->N1[a*dim+i]*p->N1[b*dim+i]; K[a*nen+b] = sum; } F[a] = p->N0[a]*f; }
+    } else {
+      double g = 0.0, G[3][3], Nn[3], nn = 0.0, h, alpha; const double *n = p->normal;
+      for (i = 0; i < dim; i++) g += p->x[i]*p->x[i];
+      for (i = 0; i < dim; i++) for (j = 0; j < dim; j++)           /* IGAPointFormInvGradGeomMap (petigapoint.c:269-294) */
+        G[i][j] = (p->E1 ? p->E1[i*dim+j] : (i == j ? 1.0 : 0.0)) / p->L[i];
+      for (i = 0; i < dim; i++) { Nn[i] = 0.0; for (j = 0; j < dim; j++) Nn[i] += G[i][j]*n[j]; nn += Nn[i]*Nn[i]; }
+      h = 2/sqrt(nn);                                               /* NormalMeshSize :58-67 */
+      alpha = 5*(p->maxdeg+1)/h;
+      for (a = 0; a < nen; a++) {
+        double dna = 0.0; for (i = 0; i < dim; i++) dna += p->N1[a*dim+i]*n[i];
+        for (b = 0; b < nen; b++) {
+          double dnb = 0.0; for (i = 0; i < dim; i++) dnb += p->N1[b*dim+i]*n[i];
+          K[a*nen+b] += - p->N0[a] * dnb;
+          K[a*nen+b] += - p->N0[b] * dna;
+          K[a*nen+b] += + alpha * p->N0[a]*p->N0[b];
+        }
+        F[a] += - dna*g;
+        F[a] += + alpha * p->N0[a]*g;
+      }
+    }
+    return 0; }
   case FORM_ELASTICITY: { /* demo/Elasticity.c:22-52; dof == dim */
     double lambda = prm[0], mu = prm[1];
     for (a = 0; a < nen; a++) for (b = 0; b < nen; b++) {
@@ -1123,6 +1160,20 @@ static int form_function(int form, const double *prm, const Point *p, double shi
     for (a = 0; a < nen; a++) {
       double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*gu[i];
       R[a] = (V ? p->N0[a]*v : 0.0) + dot - p->N0[a] * lambda * exp(u);
+    }
+    return 0; }
+  case FORM_SNES2D: { /* test/Test_SNES_2D.c:12-46 Function: L2 projection of Peaks, Poisson, reaction-diffusion, Bratu (dof 4, dim 2) */
+    double u0[4], u1[8], X, Y, peaks;
+    get_value(p,U,u0); get_grad(p,U,u1);
+    X = p->x[0]*3; Y = p->x[1]*3;
+    peaks = 3 * pow(1-X,2) * exp(-pow(X,2) - pow(Y+1,2)) - 10 * (X/5 - pow(X,3) - pow(Y,5)) * exp(-pow(X,2) - pow(Y,2))
+            - 1.0/3 * exp(-pow(X+1,2) - pow(Y,2));
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*2], Na_y = p->N1[a*2+1];
+      R[a*4+0] = Na*u0[0] - Na * peaks;
+      R[a*4+1] = Na_x*u1[2] + Na_y*u1[3] - Na * 1.0;
+      R[a*4+2] = Na*u0[2] + Na_x*u1[4] + Na_y*u1[5] - Na * 1.0;
+      R[a*4+3] = Na_x*u1[6] + Na_y*u1[7] - Na * 1.0*exp(u0[3]);
     }
     return 0; }
   case FORM_POISSON: { /* residual of demo/Poisson: R_a = grad N_a . grad u - N_a*1 (linear problem as SNES) */
@@ -1207,6 +1258,116 @@ static int form_jacobian(int form, const double *prm, const Point *p, double shi
     for (a = 0; a < nen; a++) for (b = 0; b < nen; b++) {
       double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*p->N1[b*dim+i]; K[a*nen+b] = dot; }
     return 0;
+  case FORM_SNES2D: { /* test/Test_SNES_2D.c:48-72 Jacobian */
+    double u0[4], r;
+    get_value(p,U,u0); r = u0[3];
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*2], Na_y = p->N1[a*2+1];
+      for (b = 0; b < nen; b++) {
+        double Nb = p->N0[b], Nb_x = p->N1[b*2], Nb_y = p->N1[b*2+1];
+        K[a*nen*16+0*nen*4+b*4+0] = Na*Nb;
+        K[a*nen*16+1*nen*4+b*4+1] = Na_x*Nb_x + Na_y*Nb_y;
+        K[a*nen*16+2*nen*4+b*4+2] = Na*Nb + Na_x*Nb_x + Na_y*Nb_y;
+        K[a*nen*16+3*nen*4+b*4+3] = Na_x*Nb_x + Na_y*Nb_y - Na*Nb * 1.0*exp(r);
+      }
+    }
+    return 0; }
+  }
+  return 1;
+}
+
+/* callbacks of the IE, RHS and I2 drivers (include/petiga.h:172-197): W is the third vector (U0 for IE, A for I2) */
+static int form_ext_function(int form, int slot, const double *prm, const Point *p, double a1, const double *V, double t,
+                             const double *U, double a2, const double *W, double t0, double *R)
+{
+  int a, i, nen = p->nen, dim = p->nsd; (void)a1; (void)a2; (void)t; (void)t0;
+  switch (form) {
+  case FORM_PATTERNFORMATION: { /* demo/PatternFormation.c:26-77 IEFunction; prm = {IMPLICIT, delta, D1, D2, alpha, beta, gamma, tau1, tau2} */
+    int IMPLICIT = prm[0] != 0.0;
+    double delta = prm[1], D1 = prm[2], D2 = prm[3], alpha = prm[4], beta = prm[5], gamma = prm[6], tau1 = prm[7], tau2 = prm[8];
+    double uv_t[2], uv_0[2], uv_1[4], u_t, v_t, u, v, u_x, v_x, u_y, v_y, f, g;
+    if (slot != SLOT_IEFUNCTION || dim != 2 || p->dof != 2) return 1;
+    get_value(p,V,uv_t);
+    if (IMPLICIT) get_value(p,U,uv_0); else get_value(p,W,uv_0);
+    get_grad(p,U,uv_1);
+    u_t = uv_t[0]; v_t = uv_t[1]; u = uv_0[0]; v = uv_0[1];
+    u_x = uv_1[0]; v_x = uv_1[2]; u_y = uv_1[1]; v_y = uv_1[3];
+    f = alpha*u*(1-tau1*v*v) + v*(1-tau2*u);
+    g = beta*v*(1+alpha*tau1/beta*u*v) + u*(gamma+tau2*v);
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*2], Na_y = p->N1[a*2+1];
+      R[a*2+0] = Na*u_t + delta*D1*(Na_x*u_x + Na_y*u_y) - Na*f;
+      R[a*2+1] = Na*v_t + delta*D2*(Na_x*v_x + Na_y*v_y) - Na*g;
+    }
+    return 0; }
+  case FORM_ELASTICROD: { /* demo/ElasticRodFJ.F90:19-55 I2Function: F = N rho A + E grad N . grad U; prm = {rho, E} */
+    double rho = prm[0], E = prm[1], A1, gu[3];
+    if (slot != SLOT_I2FUNCTION || p->dof != 1) return 1;
+    get_value(p,W,&A1); get_grad(p,U,gu);
+    for (a = 0; a < nen; a++) { double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*gu[i]; R[a] = p->N0[a]*rho*A1 + E*dot; }
+    return 0; }
+  case FORM_BRATU: { /* explicit form of the transient Bratu problem u_t = lap u + lambda exp(u) (demo/BratuFJ.F90 terms moved to the
+                        right-hand side): G_a = -grad N_a . grad u + N_a lambda exp(u).  No reference demo registers an RHSFunction;
+                        this form exercises IGAComputeRHSFunction (src/petigats.c:357-416) */
+    double lambda = prm[0], u, gu[3];
+    if (slot != SLOT_RHSFUNCTION || p->dof != 1) return 1;
+    get_value(p,U,&u); get_grad(p,U,gu);
+    for (a = 0; a < nen; a++) { double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*gu[i]; R[a] = -dot + p->N0[a]*lambda*exp(u); }
+    return 0; }
+  }
+  return 1;
+}
+static int form_ext_jacobian(int form, int slot, const double *prm, const Point *p, double a1, const double *V, double t,
+                             const double *U, double a2, const double *W, double t0, double *K)
+{
+  int a, b, i, j, nen = p->nen, dim = p->nsd; (void)V; (void)W; (void)a2; (void)t; (void)t0;
+  switch (form) {
+  case FORM_PATTERNFORMATION: { /* demo/PatternFormation.c:79-141 IEJacobian */
+    int IMPLICIT = prm[0] != 0.0;
+    double delta = prm[1], D1 = prm[2], D2 = prm[3], alpha = prm[4], beta = prm[5], gamma = prm[6], tau1 = prm[7], tau2 = prm[8];
+    double f_u = 0, f_v = 0, g_u = 0, g_v = 0, shift = a1;
+    if (slot != SLOT_IEJACOBIAN || dim != 2 || p->dof != 2) return 1;
+    if (IMPLICIT) {
+      double uv_0[2], u, v; get_value(p,U,uv_0); u = uv_0[0]; v = uv_0[1];
+      f_u = alpha*(1-tau1*v*v) - tau2*v;
+      f_v = -2*alpha*tau1*u*v + (1-tau2*u);
+      g_u = alpha*tau1*v*v + (gamma+tau2*v);
+      g_v = (beta+2*alpha*tau1*u*v) + tau2*u;
+    }
+    for (a = 0; a < nen; a++) {
+      double Na = p->N0[a], Na_x = p->N1[a*2], Na_y = p->N1[a*2+1];
+      for (b = 0; b < nen; b++) {
+        double Nb = p->N0[b], Nb_x = p->N1[b*2], Nb_y = p->N1[b*2+1], Kab[2][2] = {{0,0},{0,0}};
+        Kab[0][0] = shift*Na*Nb + delta*D1*(Na_x*Nb_x + Na_y*Nb_y);
+        Kab[1][1] = shift*Na*Nb + delta*D2*(Na_x*Nb_x + Na_y*Nb_y);
+        if (IMPLICIT) {
+          Kab[0][0] -= Na*f_u*Nb; Kab[0][1] -= Na*f_v*Nb;
+          Kab[1][0] -= Na*g_u*Nb; Kab[1][1] -= Na*g_v*Nb;
+          for (i = 0; i < 2; i++) for (j = 0; j < 2; j++) K[((a*2+i)*nen+b)*2+j] += Kab[i][j];
+        } else {
+          K[((a*2+0)*nen+b)*2+0] += Kab[0][0];
+          K[((a*2+1)*nen+b)*2+1] += Kab[1][1];
+        }
+      }
+    }
+    return 0; }
+  case FORM_ELASTICROD: { /* demo/ElasticRodFJ.F90:57-95 I2Jacobian: shiftA rho N_a N_b + E grad N_a . grad N_b */
+    double rho = prm[0], E = prm[1], shiftA = a1;
+    if (slot != SLOT_I2JACOBIAN || p->dof != 1) return 1;
+    for (a = 0; a < nen; a++) for (b = 0; b < nen; b++) {
+      double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*p->N1[b*dim+i];
+      K[a*nen+b] = shiftA*rho*p->N0[a]*p->N0[b] + E*dot;
+    }
+    return 0; }
+  case FORM_BRATU: { /* derivative of the RHSFunction above */
+    double lambda = prm[0], u;
+    if (slot != SLOT_RHSJACOBIAN || p->dof != 1) return 1;
+    get_value(p,U,&u);
+    for (a = 0; a < nen; a++) for (b = 0; b < nen; b++) {
+      double dot = 0; for (i = 0; i < dim; i++) dot += p->N1[a*dim+i]*p->N1[b*dim+i];
+      K[a*nen+b] = -dot + p->N0[a]*lambda*exp(u)*p->N0[b];
+    }
+    return 0; }
   }
   return 1;
 }
@@ -1253,17 +1414,38 @@ static long csr_find(const GlobalPattern *gp, int row, int col) /* the sorted-ro
 /* One full assembly over `size` emulated ranks.
    values: [nnz_blocks][dof][dof] (row-major blocks), rhs: [nrows][dof]; either may be NULL per slot.
    Ug/Vg: global vectors (PETSc ordering) or NULL.  Returns 0, or >0 on error (e.g. entry outside pattern). */
-static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const double *prm, double shift, const double *Vg,
-                    double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
+/* PETSc's stash (MatSetValues/VecSetValues on rows owned by another rank, shipped and added in Mat/VecAssemblyEnd,
+   src/petigaksp.c:197-200): entries as (flat index, value); vector entries carry index -(i)-1 */
+typedef struct { long n, cap; long *idx; double *val; int row0, row1; } Stash;
+static void stash_push(Stash *st, long idx, double v)
+{
+  if (st->n == st->cap) { st->cap = st->cap ? 2*st->cap : 4096; st->idx = (long*)realloc(st->idx, sizeof(long)*(size_t)st->cap);
+                          st->val = (double*)realloc(st->val, sizeof(double)*(size_t)st->cap); }
+  st->idx[st->n] = idx; st->val[st->n] = v; st->n++;
+}
+
+/* idx0/idx1: element index range of the rank's loop (idx1 < 0: all of it); zero: MatZeroEntries/VecZeroEntries first;
+   st: NULL, or the stash that receives contributions to rows outside [st->row0, st->row1) */
+static int assemble_ex(OIGA *o, int size, int r0, int r1, int idx0, int idx1, int zero, Stash *st, int slot, int form, const double *prm,
+                       double shift, const double *Vg, double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
 {
   int r, dof = o->dof, err = 0;
-  int want_mat = (slot == SLOT_MATRIX || slot == SLOT_SYSTEM || slot == SLOT_JACOBIAN || slot == SLOT_IJACOBIAN);
-  int want_vec = (slot == SLOT_VECTOR || slot == SLOT_SYSTEM || slot == SLOT_FUNCTION || slot == SLOT_IFUNCTION);
-  int state = (slot >= SLOT_FUNCTION), transient = (slot == SLOT_IFUNCTION || slot == SLOT_IJACOBIAN);
-  if (want_mat) memset(values, 0, sizeof(double)*(size_t)gp->nnz*dof*dof);   /* MatZeroEntries */
-  if (want_vec) memset(rhs, 0, sizeof(double)*(size_t)gp->nrows*dof);        /* VecZeroEntries */
+  int want_mat = (slot == SLOT_MATRIX || slot == SLOT_SYSTEM || slot == SLOT_JACOBIAN || slot == SLOT_IJACOBIAN ||
+                  slot == SLOT_IEJACOBIAN || slot == SLOT_RHSJACOBIAN || slot == SLOT_I2JACOBIAN);
+  int want_vec = (slot == SLOT_VECTOR || slot == SLOT_SYSTEM || slot == SLOT_FUNCTION || slot == SLOT_IFUNCTION ||
+                  slot == SLOT_IEFUNCTION || slot == SLOT_RHSFUNCTION || slot == SLOT_I2FUNCTION);
+  int state = (slot >= SLOT_FUNCTION);
+  int third = (slot == SLOT_IEFUNCTION || slot == SLOT_IEJACOBIAN || slot == SLOT_I2FUNCTION || slot == SLOT_I2JACOBIAN);
+  int transient = (slot == SLOT_IFUNCTION || slot == SLOT_IJACOBIAN || third);   /* a V vector is gathered and DelValues'ed */
+  int i2 = (slot == SLOT_I2FUNCTION || slot == SLOT_I2JACOBIAN);
+  int fixsys = (slot == SLOT_SYSTEM), fixfun = (want_vec && state), fixjac = (want_mat && state);
+  const double *Wg = o->aux_W; double shift2 = o->aux_shift2, t0 = o->aux_t0; int maxdeg = 0;
+  { int dd; for (dd = 0; dd < o->dim; dd++) if (o->axis[dd].p > maxdeg) maxdeg = o->axis[dd].p; }
+  if (third && !Wg) return 2;
+  if (want_mat && zero) memset(values, 0, sizeof(double)*(size_t)gp->nnz*dof*dof);   /* MatZeroEntries */
+  if (want_vec && zero) memset(rhs, 0, sizeof(double)*(size_t)gp->nrows*dof);        /* VecZeroEntries */
   for (r = r0; r < r1 && !err; r++) {
-    Elem e; int index, count, N, ng; double *A, *B, *K, *F, *U = NULL, *V = NULL, *arrayU = NULL, *arrayV = NULL;
+    Elem e; int index, count, N, ng; double *A, *B, *K, *F, *U = NULL, *V = NULL, *W = NULL, *arrayU = NULL, *arrayV = NULL, *arrayW = NULL;
     if (setup_rank(o, size, r)) return 1;
     elem_alloc(&e, o);
     N = e.nen*dof; ng = o->node_gwidth[0]*o->node_gwidth[1]*o->node_gwidth[2];
@@ -1275,9 +1457,12 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
       for (a = 0; a < ng; a++) for (c = 0; c < dof; c++) arrayU[(size_t)a*dof+c] = Ug[(size_t)o->lgmap[a]*dof+c];
       if (transient) { V = (double*)malloc(sizeof(double)*(size_t)N); arrayV = (double*)malloc(sizeof(double)*(size_t)ng*dof);
         for (a = 0; a < ng; a++) for (c = 0; c < dof; c++) arrayV[(size_t)a*dof+c] = Vg[(size_t)o->lgmap[a]*dof+c]; }
+      if (third) { W = (double*)malloc(sizeof(double)*(size_t)N); arrayW = (double*)malloc(sizeof(double)*(size_t)ng*dof);
+        for (a = 0; a < ng; a++) for (c = 0; c < dof; c++) arrayW[(size_t)a*dof+c] = Wg[(size_t)o->lgmap[a]*dof+c]; }
     }
     count = o->elem_width[0]*o->elem_width[1]*o->elem_width[2];
-    for (index = 0; index < count && !err; index++) {   /* IGANextElement: petigaelem.c:375-410 */
+    if (idx1 >= 0 && idx1 < count) count = idx1;
+    for (index = (idx1 >= 0 ? idx0 : 0); index < count && !err; index++) {   /* IGANextElement: petigaelem.c:375-410 */
       int i, q, a, b, idx = index, f;
       for (i = 0; i < 3; i++) { int coord = idx % o->elem_width[i]; idx = (idx - coord)/o->elem_width[i]; e.ID[i] = coord + o->elem_start[i]; }
       elem_closure(&e);
@@ -1287,6 +1472,9 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
         for (a = 0; a < e.nen; a++) for (i = 0; i < dof; i++) U[a*dof+i] = arrayU[(size_t)e.mapping[a]*dof+i];
         if (transient) { for (a = 0; a < e.nen; a++) for (i = 0; i < dof; i++) V[a*dof+i] = arrayV[(size_t)e.mapping[a]*dof+i];
           for (f = 0; f < e.nfix; f++) V[e.ifix[f]] = 0.0; }
+        if (third) { for (a = 0; a < e.nen; a++) for (i = 0; i < dof; i++) W[a*dof+i] = arrayW[(size_t)e.mapping[a]*dof+i];
+          /* I2: DelValues(A) (petigats2.c:68); IE: FixValues(U0) (petigats.c:228) */
+          for (f = 0; f < e.nfix; f++) W[e.ifix[f]] = i2 ? 0.0 : e.vfix[f]; }
         for (f = 0; f < e.nfix; f++) { e.ufix[f] = U[e.ifix[f]]; U[e.ifix[f]] = e.vfix[f]; }
       }
       { int pass;   /* IGAElementNextForm (petigaelem.c:427-447): visited boundary faces of this element first, then the interior */
@@ -1303,6 +1491,8 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
         p.atboundary = e.atboundary; p.boundary_id = e.atboundary ? 2*e.baxis + e.bside : -1; p.normal = e.normal + (size_t)q*e.nsd;
         p.N0 = e.shape[0] + (size_t)q*e.nen; p.N1 = e.shape[1] + (size_t)q*e.nen*e.nsd; p.N2 = e.shape[2] + (size_t)q*e.nen*e.nsd*e.nsd;
         p.x = e.geometry ? e.mapX[0] + (size_t)q*e.nsd : e.mapU[0] + (size_t)q*e.dim;
+        p.E1 = e.geometry ? e.mapU[1] + (size_t)q*e.dim*e.nsd : NULL; p.maxdeg = maxdeg;
+        { int dd; for (dd = 0; dd < 3; dd++) p.L[dd] = o->basis[dd].detJac[e.ID[dd]]; }
         if (want_mat) memset(K, 0, sizeof(double)*(size_t)N*N);
         memset(F, 0, sizeof(double)*(size_t)N);
         switch (slot) {
@@ -1315,6 +1505,10 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
         case SLOT_IFUNCTION: ret = form_function(form, prm, &p, shift, V, t, U, F); break;
         case SLOT_JACOBIAN:  ret = form_jacobian(form, prm, &p, 0.0, NULL, 0.0, U, K, 0); break;
         case SLOT_IJACOBIAN: ret = form_jacobian(form, prm, &p, shift, V, t, U, K, 1); break;
+        case SLOT_IEFUNCTION: case SLOT_I2FUNCTION: ret = form_ext_function(form, slot, prm, &p, shift, V, t, U, shift2, W, t0, F); break;
+        case SLOT_RHSFUNCTION: ret = form_ext_function(form, slot, prm, &p, 0.0, NULL, t, U, 0.0, NULL, 0.0, F); break;
+        case SLOT_IEJACOBIAN: case SLOT_I2JACOBIAN: ret = form_ext_jacobian(form, slot, prm, &p, shift, V, t, U, shift2, W, t0, K); break;
+        case SLOT_RHSJACOBIAN: ret = form_ext_jacobian(form, slot, prm, &p, 0.0, NULL, t, U, 0.0, NULL, 0.0, K); break;
         }
         if (ret) { err = 10; break; }
         if (want_mat) for (i = 0; i < N*N; i++) A[i] += K[i] * JW;
@@ -1323,7 +1517,7 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
       } e.atboundary = 0; }
       if (err) break;
       /* fix-up: petigaelem.c:1360-1389 (System), :1441-1463 (Function), :1483-1501 (Jacobian) */
-      if (slot == SLOT_SYSTEM) {
+      if (fixsys) {
         for (f = 0; f < e.nflux; f++) B[e.iflux[f]] += e.vflux[f];
         for (f = 0; f < e.nfix; f++) {
           int k = e.ifix[f]; double v = e.vfix[f];
@@ -1332,10 +1526,10 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
           for (i = 0; i < N; i++) A[k*N+i] = 0.0;
           A[k*N+k] = 1.0; B[k] = v;
         }
-      } else if (slot == SLOT_FUNCTION || slot == SLOT_IFUNCTION) {
+      } else if (fixfun) {
         for (f = 0; f < e.nflux; f++) B[e.iflux[f]] -= e.vflux[f];
         for (f = 0; f < e.nfix; f++) B[e.ifix[f]] = e.ufix[f] - e.vfix[f];
-      } else if (slot == SLOT_JACOBIAN || slot == SLOT_IJACOBIAN) {
+      } else if (fixjac) {
         for (f = 0; f < e.nfix; f++) {
           int k = e.ifix[f];
           for (i = 0; i < N; i++) A[i*N+k] = 0.0;
@@ -1346,17 +1540,20 @@ static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const
       /* scatter: MatSetValues[Blocked]Local / VecSetValues[Blocked]Local with ADD_VALUES (petigaelem.c:1525-1559) */
       for (a = 0; a < e.nen; a++) {
         int grow = o->lgmap[e.mapping[a]], ii, jj;
-        if (want_vec) for (ii = 0; ii < dof; ii++) rhs[(size_t)grow*dof+ii] += B[a*dof+ii];
+        int off = st && (grow < st->row0 || grow >= st->row1);   /* row of another rank: goes to the stash */
+        if (want_vec) for (ii = 0; ii < dof; ii++) {
+          if (off) stash_push(st, -((long)grow*dof+ii)-1, B[a*dof+ii]); else rhs[(size_t)grow*dof+ii] += B[a*dof+ii]; }
         if (want_mat) for (b = 0; b < e.nen; b++) {
           int gcol = o->lgmap[e.mapping[b]]; long pos = csr_find(gp, grow, gcol);
           if (pos < 0) { err = 20; break; }            /* MAT_NEW_NONZERO_LOCATION_ERR (petigamat.c:538) */
-          for (ii = 0; ii < dof; ii++) for (jj = 0; jj < dof; jj++)
-            values[((size_t)pos*dof+ii)*dof+jj] += A[((size_t)(a*dof+ii))*N + b*dof+jj];
+          for (ii = 0; ii < dof; ii++) for (jj = 0; jj < dof; jj++) {
+            if (off) stash_push(st, ((long)pos*dof+ii)*dof+jj, A[((size_t)(a*dof+ii))*N + b*dof+jj]);
+            else values[((size_t)pos*dof+ii)*dof+jj] += A[((size_t)(a*dof+ii))*N + b*dof+jj]; }
         }
         if (err) break;
       }
     }
-    free(A); free(B); free(K); free(F); free(U); free(V); free(arrayU); free(arrayV);
+    free(A); free(B); free(K); free(F); free(U); free(V); free(W); free(arrayU); free(arrayV); free(arrayW);
     elem_free(&e);
   }
   return err;
@@ -1412,6 +1609,8 @@ void oiga_set_fixtable(OIGA *o, const double *Uglobal, long n)
   if (Uglobal) { o->fixtable_glob = (double*)malloc((size_t)n*sizeof(double)); memcpy(o->fixtable_glob, Uglobal, (size_t)n*sizeof(double)); o->fixtable = 1; } }
 
 int oiga_setup(OIGA *o, int size, int rank) { return setup_rank(o, size, rank); }
+/* third vector (U0 of the IE drivers, A of the I2 drivers; global PETSc ordering), second shift, second time */
+void oiga_set_aux(OIGA *o, double shift2, double t0, const double *Wg) { o->aux_shift2 = shift2; o->aux_t0 = t0; o->aux_W = Wg; }
 
 /* info[0..]: order, then per axis: p, m, nnp, nel, nqp, nen, proc_size, proc_rank, elem_start, elem_width,
    node_lstart, node_lwidth, node_gstart, node_gwidth, geom_size  (15 per axis) */
@@ -1444,9 +1643,41 @@ const int *oiga_pattern_rowptr(const GlobalPattern *gp) { return gp->rowptr; }
 const int *oiga_pattern_colidx(const GlobalPattern *gp) { return gp->colidx; }
 const int *oiga_pattern_rank_rowstart(const GlobalPattern *gp) { return gp->rank_rowstart; }
 
+static int assemble(OIGA *o, int size, int r0, int r1, int slot, int form, const double *prm, double shift, const double *Vg,
+                    double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
+{ return assemble_ex(o, size, r0, r1, 0, -1, 1, NULL, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
 int oiga_assemble(OIGA *o, int size, int slot, int form, const double *prm, double shift, const double *Vg,
                   double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
 { return assemble(o, size, 0, size, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
+/* elements [idx0, idx1) of the ONE-rank element loop, ADDED into caller-zeroed arrays: lets the test harness split the loop
+   over host threads (tests/par_oracle.py) while keeping the one-rank numbering */
+int oiga_assemble_range(OIGA *o, int idx0, int idx1, int slot, int form, const double *prm, double shift, const double *Vg,
+                        double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs)
+{ return assemble_ex(o, 1, 0, 1, idx0, idx1, 0, NULL, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs); }
+/* One emulated MPI rank the way PETSc runs it: rows it owns are added straight into the (shared, caller-zeroed) global
+   arrays, rows of other ranks go to its stash; oiga_stash_apply is the receiving side of Mat/VecAssemblyEnd.  With one
+   thread per rank nothing races: a rank only writes its own row range, and applies only entries inside it. */
+void *oiga_stash_create(void) { return calloc(1, sizeof(Stash)); }
+void  oiga_stash_destroy(void *p) { Stash *st = (Stash*)p; if (!st) return; free(st->idx); free(st->val); free(st); }
+long  oiga_stash_count(const void *p) { return ((const Stash*)p)->n; }
+int oiga_assemble_rank_stash(OIGA *o, int size, int rank, int slot, int form, const double *prm, double shift, const double *Vg,
+                             double t, const double *Ug, const GlobalPattern *gp, double *values, double *rhs, void *stash)
+{
+  Stash *st = (Stash*)stash;
+  st->n = 0; st->row0 = gp->rank_rowstart[rank]; st->row1 = gp->rank_rowstart[rank+1];
+  return assemble_ex(o, size, rank, rank+1, 0, -1, 0, st, slot, form, prm, shift, Vg, t, Ug, gp, values, rhs);
+}
+void oiga_stash_apply(const void *stash, int dof, const GlobalPattern *gp, int rank, double *values, double *rhs)
+{
+  const Stash *st = (const Stash*)stash; long k;
+  const long r0 = gp->rank_rowstart[rank], r1 = gp->rank_rowstart[rank+1];
+  const long v0 = (long)gp->rowptr[r0]*dof*dof, v1 = (long)gp->rowptr[r1]*dof*dof;
+  for (k = 0; k < st->n; k++) {
+    long i = st->idx[k];
+    if (i >= 0) { if (i >= v0 && i < v1) values[i] += st->val[k]; }
+    else { i = -i-1; if (i >= r0*dof && i < r1*dof) rhs[i] += st->val[k]; }
+  }
+}
 /* the element loop of ONE emulated rank (its contributions only, into the global arrays): lets the CPU baseline run
    the ranks in parallel processes the way mpiexec -n size would */
 int oiga_assemble_rank(OIGA *o, int size, int rank, int slot, int form, const double *prm, double shift, const double *Vg,

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "pc_plan.h"
 
@@ -154,6 +155,24 @@ __global__ void fixtable_scatter_kernel(const int* __restrict__ localrow, const 
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ng * dof; i += (size_t)gridDim.x * blockDim.x) {
     const size_t g = i / dof;
     out[i] = loc[(size_t)localrow[g] * dof + (i - g * dof)];
+  }
+}
+
+// ||a - b||^2 and ||b||^2 over n doubles: per-CTA partial sums in a fixed order (deterministic), finished on the host.
+// Used by the full-size parity tests to compare two 5.9 GB value arrays without moving them off the device.
+__global__ void __launch_bounds__(256) diff_norm_kernel(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* __restrict__ part) {
+  __shared__ double sd[8], sr[8];
+  double d2 = 0.0, r2 = 0.0;
+  const size_t chunk = (n + gridDim.x - 1) / gridDim.x, lo = (size_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const double x = a[i], y = b[i]; d2 = fma(x - y, x - y, d2); r2 = fma(y, y, r2); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { d2 += __shfl_xor_sync(0xffffffffu, d2, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o); }
+  if ((threadIdx.x & 31) == 0) { sd[threadIdx.x >> 5] = d2; sr[threadIdx.x >> 5] = r2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0, y = 0.0;
+    for (int w = 0; w < 8; w++) { x += sd[w]; y += sr[w]; }
+    part[2 * blockIdx.x] = x; part[2 * blockIdx.x + 1] = y;
   }
 }
 
@@ -316,6 +335,7 @@ int petiga_cuda_get_stat(petiga_cuda_plan* P, const char* name, double* value) {
   if (!strcmp(name, "last_path")) { *value = (double)P->last_path; return 0; }
   if (!strcmp(name, "last_impl")) { *value = (double)P->last_impl; return 0; }
   if (!strcmp(name, "last_kernel_ms")) { *value = P->last_kernel_ms; return 0; }
+  if (!strcmp(name, "last_flops")) { *value = P->last_flops; return 0; }
   if (!strcmp(name, "num_sms")) { *value = P->num_sms; return 0; }
   if (!strcmp(name, "nghostrows")) { *value = P->L.nghostrows; return 0; }
   if (!strcmp(name, "nnz_loc")) { *value = (double)P->L.nnz_loc; return 0; }
@@ -534,6 +554,7 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   if (P->path == PETIGA_PATH_KRONECKER && !kron_ok) { set_error("compute: separable path not applicable (geometry, state or non-separable form)"); return PETIGA_CUDA_ERR_SUP; }
   const bool use_kron = kron_ok && P->path != PETIGA_PATH_QUADRATURE;
   P->last_path = use_kron ? PETIGA_PATH_KRONECKER : PETIGA_PATH_QUADRATURE;
+  P->last_flops = 0;
 
   cudaEventRecord(P->ev0, P->stream);
   bool quad_mat = want_mat;   // does the quadrature kernel still have to produce the matrix?
@@ -721,6 +742,22 @@ int petiga_cuda_measure_fp64(int device, double seconds, double* tflops_burst, d
   if (tflops_sustained) *tflops_sustained = sus_flop / (ms * 1e-3) / 1e12;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(d);
+  return 0;
+}
+
+int petiga_cuda_diff_norm2(const double* d_a, const double* d_b, size_t n, double* diff2, double* ref2) {
+  if (!d_a || !d_b || !diff2 || !ref2) return PETIGA_CUDA_ERR_ARG;
+  const int blocks = 1184;
+  double* part = nullptr;
+  PC_CUDA(cudaMalloc(&part, 2 * blocks * sizeof(double)));
+  diff_norm_kernel<<<blocks, 256>>>(d_a, d_b, n, part);
+  std::vector<double> h(2 * blocks);
+  cudaError_t e = cudaMemcpy(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(part);
+  if (e != cudaSuccess) return cuda_fail(e, "diff_norm2");
+  double x = 0.0, y = 0.0;
+  for (int b = 0; b < blocks; b++) { x += h[2 * b]; y += h[2 * b + 1]; }
+  *diff2 = x; *ref2 = y;
   return 0;
 }
 

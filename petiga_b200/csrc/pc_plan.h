@@ -79,6 +79,7 @@ struct petiga_cuda_plan {
   int last_path = 0;
   int last_impl = 0;
   double last_kernel_ms = 0;
+  double last_flops = 0;          // FP64 operations the last quadrature launch executes (analytic count by its launcher)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 148;
 };

@@ -34,6 +34,8 @@ int launch_one(petiga_cuda_plan* Pl, KParams prm) {
   auto kern = quad_kernel<DIM, P, DOF, TM>;
   PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (prm.nelem + epb - 1) / epb;
+  // FP64 operations executed: the contraction K_e += Psi^T T (2 per FMA), the T-builder and the element vector
+  Pl->last_flops = (double)prm.nelem * nqp * (2.0 * NA * Cfg::M * Cfg::N + 2.0 * NA * NA * Cfg::N + 2.0 * NV * Cfg::M * DOF);
   if (blocks > 0) {
     kern<<<blocks, threads, smem, Pl->stream>>>(prm);
     PC_CUDA(cudaGetLastError());

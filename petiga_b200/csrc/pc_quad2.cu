@@ -161,6 +161,18 @@ int launch_sf_nq(petiga_cuda_plan* Pl, SFParams& sp) {
   constexpr bool kHas4 = (Cfg::THREADS == 256 && Cfg::G == 256 && DOF == 1 && NQ > 0);
   const bool use4 = kHas4 && epb == 1 && (smem + 1024) * 4 <= 227 * 1024;
   const int blocks = (base.nelem + epb - 1) / epb;
+  {  // FP64 operations this launch executes (2 per FMA), from the same lists the kernel walks
+    const SFLists& l = sp.l;
+    const double n0 = Cfg::n0, n1 = Cfg::n1, n2 = Cfg::n2, q0 = nq[0], q1 = nq[1], q2 = nq[2], nqp = q0 * q1 * q2, G = n0 * n0 * n1 * n1;
+    int nij = 0;
+    for (int ij = 0; ij < DOF * DOF; ij++) nij += (l.ijmask >> ij) & 1;
+    double f = 0.0;
+    if (NA > 0) f += nij * (2.0 * nqp * n0 * n0 * l.npairs + 2.0 * G * q2 * l.ng1 * q1 + G * q2 * l.ng2 * (n2 + 2.0 * n2 * n2) +
+                            (sp.const_dp ? 1.0 : 2.0 * NA * NA) * l.npairs * nqp);
+    f += 2.0 * l.nev * (q0 * n1 * n2 * n0 + q0 * q1 * n2 * n1 + nqp * n2);                                   // field evaluation
+    if (NV > 0) f += 2.0 * DOF * l.NT * (q2 * q1 * n0 * q0 + q2 * n1 * n0 * q1 + n0 * n1 * n2 * q2) + 2.0 * nqp * DOF * l.NT * NV;
+    Pl->last_flops = f * base.nelem;
+  }
   auto go = [&](auto kern) -> int {
     PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (blocks > 0) {

@@ -71,3 +71,24 @@ def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0,
         else:
             assert errs["F"] <= tol, ("vector", errs["F"])
     return res, errs
+
+
+def check_against_parallel_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, tol=1e-12, quad_impl=None,
+                                  T=None):
+    """Same as check_against_oracle, with the oracle's one-rank element loop split over host threads (tests/par_oracle.py):
+    for the cases at or near BASELINE size, where one thread would take minutes."""
+    from tests.par_oracle import assemble_parallel
+    rp_o, ci_o, Ko, Fo = assemble_parallel(case, slot, form, params, T=T, shift=shift, V=V, t=t, U=U)
+    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, quad_impl=quad_impl)
+    errs = {}
+    if Ko is not None:
+        dof = case.dof
+        if res["baij"] or dof == 1:
+            assert np.array_equal(res["rowptr"], rp_o) and np.array_equal(res["colidx"], ci_o)
+        exp = oracle_to_layout(Ko, rp_o, dof, res["baij"])
+        errs["K"] = rel_frobenius(res["values"], exp)
+        assert errs["K"] <= tol, ("matrix", errs["K"])
+    if Fo is not None:
+        errs["F"] = rel_frobenius(res["rhs"], Fo.reshape(-1))
+        assert errs["F"] <= tol, ("vector", errs["F"])
+    return res, errs

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.common import oracle_to_layout, rel_frobenius
+from tests.common import Case, oracle_to_layout, rel_frobenius
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -50,3 +50,26 @@ def test_device_matches_golden(name):
         assert rel_frobenius(res["values"], exp) <= 1e-12
     if name + "/rhs" in BLOB.files:
         assert rel_frobenius(res["rhs"], BLOB[name + "/rhs"].reshape(-1)) <= 1e-12
+
+
+def test_oracle_reproduces_multirank_golden():
+    """tests/golden/multirank_cases.npz (what bench.py's "parity" key and the N-rank runs are compared with) is the oracle's
+    one-rank output; a changed oracle must fail here before it silently changes what the GPUs are checked against."""
+    from petiga_b200.cases import state_vectors
+    from petiga_b200.parity import GOLDEN, golden_cases
+    gold = np.load(GOLDEN)
+    for name, (pc, slot, form, params, state, shift) in golden_cases().items():
+        case = Case.__new__(Case)
+        case.__dict__.update(pc.__dict__)
+        o = case.oracle()
+        o.setup()
+        rp, ci, _ = o.pattern(1)
+        assert np.array_equal(rp, gold[name + "/rowptr"]) and np.array_equal(ci, gold[name + "/colidx"])
+        U = V = None
+        if state:
+            U, V = state_vectors((len(rp) - 1) * case.dof)
+        K, F = o.assemble(slot, form, params, size=1, shift=shift, U=U, V=V)
+        if K is not None:
+            assert rel_frobenius(K, gold[name + "/K"]) <= 1e-14
+        if F is not None:
+            assert rel_frobenius(F, gold[name + "/F"]) <= 1e-14

@@ -291,53 +291,7 @@ def test_poisson3d_separable_equals_quadrature_midsize(p, N):
     assert rel_frobenius(a["values"], b["values"]) <= TOL and rel_frobenius(a["rhs"], b["rhs"]) <= TOL
 
 
-# ---- size-independent properties at BASELINE's full cfg-2 size (the oracle cannot run 128^3 in seconds) -------
-def test_cfg2_full_size_properties():
-    import petiga_b200 as pb
-    N, p = 128, 3
-    g = pb.IGA(3, 1)
-    for d in range(3):
-        g.AxisInitUniform(d, p, N)
-    g.SetUp()
-    for d in range(3):
-        for s in range(2):
-            g.SetBoundaryValue(d, s, 0, 1.0)
-    g.SetForm("SYSTEM", "POISSON")
-    A, B = g.CreateMat(), g.CreateVec()
-    assert A.nrows == 131 ** 3 and A.nnz == 905 ** 3 == 741217625          # SURVEY 8 size table
-    sums = {}
-    for path in ("auto", "quadrature"):
-        g.SetOption("path", {"auto": 0, "quadrature": 1}[path])
-        g.ComputeSystem(A, B)
-        rhs = B.get()
-        # total load: sum F = volume of free part + Dirichlet rows count*value; compare both paths + closed forms
-        sums[path] = rhs
-    assert np.allclose(sums["auto"], sums["quadrature"], rtol=1e-12, atol=1e-15)
-    rhs = sums["auto"].reshape(131, 131, 131)
-    # a corner node sits in 1 element, an edge node next to it in 2, a face-interior node in up to 16 (4x4)
-    assert rhs[0, 0, 0] == 1.0 and rhs[0, 0, 1] == 2.0 and rhs[0, 0, 2] == 3.0 and rhs[0, 0, 64] == 4.0
-    assert rhs[0, 64, 64] == 16.0
-    # sample rows of the matrix through the device pattern: interior row sums of a stiffness matrix vanish,
-    # fixed rows are count * identity
-    import ctypes as C
-    plan = g.plan()
-    L = pb.load_cuda()
-    rp = np.empty(A.nrows + 1, dtype=np.int32)
-    L.petiga_cuda_plan_pattern_host(plan, 0, rp.ctypes.data_as(C.POINTER(C.c_int)), None)
-    vals_ptr = A.device_ptr()
-    def row_values(r):
-        n = int(rp[r + 1] - rp[r])
-        out = np.empty(n)
-        L.petiga_cuda_memcpy_d2h(out.ctypes.data_as(C.c_void_p), C.c_void_p(vals_ptr + 8 * int(rp[r])), C.c_size_t(8 * n))
-        return out
-    idx = lambda i, j, k: i + 131 * (j + 131 * k)
-    v = row_values(idx(64, 64, 64))
-    assert len(v) == 343 and abs(v.sum()) < 1e-12 * np.abs(v).sum()
-    v = row_values(idx(5, 70, 9))
-    assert abs(v.sum()) < 1e-12 * np.abs(v).sum()
-    v = row_values(idx(0, 64, 64))
-    assert np.count_nonzero(v) == 1 and v.sum() == 16.0
-    A.destroy(); B.destroy()
+# (full-size and near-full-size parity: tests/test_gpu_fullsize.py)
 
 
 # ---- multi-GPU: ghost-row exchange + state halo over NCCL (skipped on a single-GPU box) ------------------------

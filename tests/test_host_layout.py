@@ -247,3 +247,20 @@ def test_headers_are_plain_c_and_the_readme_example_links(tmp_path):
                                "-L", lib, "-lpetiga_host", "-lpetiga_cuda", "-Wl,-rpath," + lib, "-o", exe])
         rc = subprocess.run([exe]).returncode
         assert rc == (0 if torch.cuda.is_available() else 3), (src, rc)
+
+
+def test_handles_survive_ctypes_above_4gb():
+    """Vec/Mat handles must cross ctypes as 64-bit pointers.  A bare Python int is converted to a C int and a
+    pointer such as 0x55aa12345678 would arrive truncated; the wrappers keep c_void_p objects."""
+    import ctypes as C
+    from petiga_b200.iga import Mat, Vec, _vp
+    big = 0x55AA12345678
+    v = Vec(None, big)
+    assert isinstance(v.h, C.c_void_p) and v.h.value == big
+    labs = C.CDLL(None).labs
+    labs.restype = C.c_long
+    assert labs(v.h) == big              # what a library function receives when handed the wrapper's handle
+    assert labs(_vp(C.c_void_p(big))) == big
+    m = Mat.__new__(Mat)
+    m.h = _vp(big)
+    assert m.h.value == big
