@@ -57,7 +57,10 @@ enum {
 /* the seven driver slots (which IGACompute* is being replaced) */
 enum {
   PETIGA_SLOT_VECTOR = 0, PETIGA_SLOT_MATRIX = 1, PETIGA_SLOT_SYSTEM = 2, PETIGA_SLOT_FUNCTION = 3,
-  PETIGA_SLOT_JACOBIAN = 4, PETIGA_SLOT_IFUNCTION = 5, PETIGA_SLOT_IJACOBIAN = 6, PETIGA_NSLOTS = 7
+  PETIGA_SLOT_JACOBIAN = 4, PETIGA_SLOT_IFUNCTION = 5, PETIGA_SLOT_IJACOBIAN = 6,
+  /* the implicit-explicit, explicit and second-order TS drivers (src/petigats.c:182-477, src/petigats2.c:23-175) */
+  PETIGA_SLOT_IEFUNCTION = 7, PETIGA_SLOT_IEJACOBIAN = 8, PETIGA_SLOT_RHSFUNCTION = 9, PETIGA_SLOT_RHSJACOBIAN = 10,
+  PETIGA_SLOT_I2FUNCTION = 11, PETIGA_SLOT_I2JACOBIAN = 12, PETIGA_NSLOTS = 13
 };
 
 /* built-in device forms = the user callbacks of the reference's demos/tests */
@@ -75,7 +78,13 @@ enum {
   PETIGA_FORM_NEUMANN = 9,        /* demo/Neumann.c:28-45 SystemGalerkin: Laplace + f = 4 pi^2 sum_i sin(2 pi x_i)   */
   PETIGA_FORM_CAHNHILLIARD3D = 10, /* demo/CahnHilliard3D.c:54-169 Residual/Tangent; params = {theta, L0, lambda}          */
   PETIGA_FORM_CONVTEST = 11,      /* test/ConvTest.c:30-69 Galerkin (reaction-diffusion); params = {c, k}                */
-  PETIGA_NFORMS = 12
+  PETIGA_FORM_SNES2D = 12,        /* test/Test_SNES_2D.c:12-72 Function/Jacobian (dim 2, dof 4)                            */
+  PETIGA_FORM_PATTERNFORMATION = 13, /* demo/PatternFormation.c:26-141 IEFunction/IEJacobian (dim 2, dof 2);
+                                        params = {IMPLICIT, delta, D1, D2, alpha, beta, gamma, tau1, tau2}                 */
+  PETIGA_FORM_ELASTICROD = 14,    /* demo/ElasticRodFJ.F90 I2Function/I2Jacobian; params = {rho, E}                        */
+  PETIGA_FORM_NITSCHE = 15,       /* demo/NitscheMethod.c:70-119 System: Poisson inside, Nitsche matrix + vector terms on the
+                                     faces enabled with petiga_cuda_set_boundary_form                                       */
+  PETIGA_NFORMS = 16              /* PETIGA_FORM_BRATU also provides RHSFunction/RHSJacobian (its explicit form)            */
 };
 
 /* built-in Scalar callbacks of petiga_cuda_compute_scalar (IGAComputeScalar, src/petigacomp.c:35-96) */
@@ -95,6 +104,9 @@ enum {
   PETIGA_PATH_QUADRATURE = 1,     /* always the per-element quadrature kernels (the reference's formulation)       */
   PETIGA_PATH_KRONECKER = 2       /* force the separable path; PETIGA_CUDA_ERR_SUP when not applicable             */
 };
+/* quadrature kernel selection (petiga_cuda_set_option "quad_impl"): -1 = by element size; 0 = sum-factorised; 1 = pair loop;
+   2 = generic runtime-degree kernel (mixed degrees, degree <= 8, dof <= 8, second derivatives on mapped / NURBS geometry,
+   the IE/RHS/I2 drivers, boundary-integral matrix terms) */
 
 typedef struct petiga_cuda_plan petiga_cuda_plan;
 
@@ -179,6 +191,13 @@ int petiga_cuda_plan_lgmap_host(petiga_cuda_plan *plan, int *lgmap);   /* ghost 
    petiga_cuda_finish, exactly as the reference drivers leave their Mat/Vec. */
 int petiga_cuda_compute(petiga_cuda_plan *plan, int slot, int block, double shift, const double *V, double t,
                         const double *U, double *values, double *rhs);
+/* The drivers with a third vector and a second shift / time (slots 7..12):
+     IEFunction/IEJacobian (shift, V, t, U, t0, W = U0)      src/petigats.c:182-355
+     RHSFunction/RHSJacobian (t, U)                           src/petigats.c:357-477
+     I2Function/I2Jacobian (shift = shiftA, W = A, shift2 = shiftV, V, t, U)   src/petigats2.c:23-175
+   Slots 0..6 ignore the extra arguments (petiga_cuda_compute is this call with them zero). */
+int petiga_cuda_compute_ext(petiga_cuda_plan *plan, int slot, int block, double shift, const double *V, double t,
+                            const double *U, double shift2, const double *W, double t0, double *values, double *rhs);
 int petiga_cuda_finish(petiga_cuda_plan *plan);
 
 /* IGAComputeScalar (src/petigacomp.c:35-96): S[k] = sum over all ranks, elements and quadrature points of

@@ -67,6 +67,14 @@ typedef PetscErrorCode (*IGAFormJacobian)(IGAPoint p, const PetscScalar *U, Pets
 typedef PetscErrorCode (*IGAFormIFunction)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *F, void *ctx);
 typedef PetscErrorCode (*IGAFormIJacobian)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *J, void *ctx);
 
+/* include/petiga.h:172-197: second-order (I2), implicit-explicit (IE) and explicit (RHS) TS callbacks */
+typedef PetscErrorCode (*IGAFormI2Function)(IGAPoint p, PetscReal a, const PetscScalar *A, PetscReal v, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormI2Jacobian)(IGAPoint p, PetscReal a, const PetscScalar *A, PetscReal v, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscScalar *J, void *ctx);
+typedef PetscErrorCode (*IGAFormIEFunction)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscReal t0, const PetscScalar *U0, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormIEJacobian)(IGAPoint p, PetscReal a, const PetscScalar *V, PetscReal t, const PetscScalar *U, PetscReal t0, const PetscScalar *U0, PetscScalar *J, void *ctx);
+typedef PetscErrorCode (*IGAFormRHSFunction)(IGAPoint p, PetscReal t, const PetscScalar *U, PetscScalar *F, void *ctx);
+typedef PetscErrorCode (*IGAFormRHSJacobian)(IGAPoint p, PetscReal t, const PetscScalar *U, PetscScalar *J, void *ctx);
+
 typedef PetscErrorCode (*IGAFormScalar)(IGAPoint p, const PetscScalar *U, PetscInt n, PetscScalar *S, void *ctx);   /* petiga.h:172 */
 typedef PetscErrorCode (*IGAFormExact)(IGAPoint p, PetscInt k, PetscScalar V[], void *ctx);                          /* petiga.h:173 */
 
@@ -93,6 +101,19 @@ PetscErrorCode IGADeviceForm_Bratu_Function(IGAPoint, const PetscScalar *, Petsc
 PetscErrorCode IGADeviceForm_Bratu_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_IFunction(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
 PetscErrorCode IGADeviceForm_Bratu_IJacobian(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+
+PetscErrorCode IGADeviceForm_Nitsche_System(IGAPoint, PetscScalar *, PetscScalar *, void *);             /* demo/NitscheMethod.c:70-119 (interior + face terms) */
+PetscErrorCode IGADeviceForm_SNES2D_Function(IGAPoint, const PetscScalar *, PetscScalar *, void *);     /* test/Test_SNES_2D.c:12-46 (dim 2, dof 4) */
+PetscErrorCode IGADeviceForm_SNES2D_Jacobian(IGAPoint, const PetscScalar *, PetscScalar *, void *);     /* test/Test_SNES_2D.c:48-72 */
+/* demo/PatternFormation.c:26-141; ctx: the demo's AppCtx {PetscBool IMPLICIT; PetscReal delta, D1, D2, alpha, beta, gamma, tau1, tau2} */
+PetscErrorCode IGADeviceForm_PatternFormation_IEFunction(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_PatternFormation_IEJacobian(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+/* demo/ElasticRodFJ.F90 (ElasticRod_IFunction / ElasticRod_IJacobian); ctx: {rho, E} */
+PetscErrorCode IGADeviceForm_ElasticRod_I2Function(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_ElasticRod_I2Jacobian(IGAPoint, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscReal, const PetscScalar *, PetscScalar *, void *);
+/* explicit form of the transient Bratu problem (no reference demo registers an RHSFunction); ctx: {lambda} */
+PetscErrorCode IGADeviceForm_Bratu_RHSFunction(IGAPoint, PetscReal, const PetscScalar *, PetscScalar *, void *);
+PetscErrorCode IGADeviceForm_Bratu_RHSJacobian(IGAPoint, PetscReal, const PetscScalar *, PetscScalar *, void *);
 
 /* Scalar / Exact sentinels for IGAComputeScalar and IGAComputeErrorNorm (src/petigacomp.c:35-186) */
 PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar *, PetscInt, PetscScalar *, void *);  /* demo/CahnHilliard2D.c:43-58; ctx: {theta, alpha, cbar} */
@@ -151,6 +172,12 @@ PetscErrorCode IGASetFormFunction(IGA iga, IGAFormFunction Function, void *ctx);
 PetscErrorCode IGASetFormJacobian(IGA iga, IGAFormJacobian Jacobian, void *ctx);
 PetscErrorCode IGASetFormIFunction(IGA iga, IGAFormIFunction IFunction, void *ctx);
 PetscErrorCode IGASetFormIJacobian(IGA iga, IGAFormIJacobian IJacobian, void *ctx);
+PetscErrorCode IGASetFormI2Function(IGA iga, IGAFormI2Function IFunction, void *ctx);      /* include/petiga.h:309-314 */
+PetscErrorCode IGASetFormI2Jacobian(IGA iga, IGAFormI2Jacobian IJacobian, void *ctx);
+PetscErrorCode IGASetFormIEFunction(IGA iga, IGAFormIEFunction IEFunction, void *ctx);
+PetscErrorCode IGASetFormIEJacobian(IGA iga, IGAFormIEJacobian IEJacobian, void *ctx);
+PetscErrorCode IGASetFormRHSFunction(IGA iga, IGAFormRHSFunction RHSFunction, void *ctx);
+PetscErrorCode IGASetFormRHSJacobian(IGA iga, IGAFormRHSJacobian RHSJacobian, void *ctx);
 
 /* the IGAForm object API of the demos that use it (demo/BoundaryIntegral.c:163-172): include/petiga.h:270-289 */
 PetscErrorCode IGAGetForm(IGA iga, IGAForm *form);
@@ -188,6 +215,13 @@ PetscErrorCode IGAComputeFunction(IGA iga, Vec U, Vec F);
 PetscErrorCode IGAComputeJacobian(IGA iga, Vec U, Mat J);
 PetscErrorCode IGAComputeIFunction(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Vec F);
 PetscErrorCode IGAComputeIJacobian(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, Mat J);
+/* the IE / RHS / I2 drivers: include/petiga.h:852-877, src/petigats.c:182-477, src/petigats2.c:23-175 */
+PetscErrorCode IGAComputeIEFunction(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, PetscReal t0, Vec U0, Vec F);
+PetscErrorCode IGAComputeIEJacobian(IGA iga, PetscReal a, Vec V, PetscReal t, Vec U, PetscReal t0, Vec U0, Mat J);
+PetscErrorCode IGAComputeRHSFunction(IGA iga, PetscReal t, Vec U, Vec F);
+PetscErrorCode IGAComputeRHSJacobian(IGA iga, PetscReal t, Vec U, Mat J);
+PetscErrorCode IGAComputeI2Function(IGA iga, PetscReal a, Vec A, PetscReal v, Vec V, PetscReal t, Vec U, Vec F);
+PetscErrorCode IGAComputeI2Jacobian(IGA iga, PetscReal a, Vec A, PetscReal v, Vec V, PetscReal t, Vec U, Mat J);
 
 /* ---- functionals: src/petigacomp.c:35-186.  vecU may be NULL; Scalar/Exact must be one of the sentinels above
         (Exact may be NULL: norms of the discrete field) ---- */

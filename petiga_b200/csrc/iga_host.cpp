@@ -72,7 +72,7 @@ struct _p_IGA {
   Vec fixtable = nullptr;
   std::vector<double> fixtable_local;
   bool bc_dirty = true, geom_dirty = true;
-  struct Slot { int form = -1; double prm[8] = {0}; int nprm = 0; bool dirty = false; } slots[PETIGA_NSLOTS];
+  struct Slot { int form = -1; double prm[12] = {0}; int nprm = 0; bool dirty = false; } slots[PETIGA_NSLOTS];
   petiga_layout* layout = nullptr;
   petiga_cuda_plan* plan = nullptr;
   void* stream = nullptr;
@@ -268,6 +268,7 @@ PetscErrorCode ensure_plan(IGA g) {
   return 0;
 }
 
+// swap01 = 1: AppCtx is {mu, lambda} (demo/Elasticity.c); swap01 = 2: AppCtx starts with a PetscBool (demo/PatternFormation.c:14-24)
 struct FormEntry { const void* fn; int slot; int form; int nprm; int swap01; };
 #define FN(f) ((const void*)(f))
 const FormEntry* lookup_form(const void* fn, int slot) {
@@ -293,6 +294,15 @@ const FormEntry* lookup_form(const void* fn, int slot) {
       {FN(IGADeviceForm_Bratu_Jacobian), PETIGA_SLOT_JACOBIAN, PETIGA_FORM_BRATU, 1, 0},
       {FN(IGADeviceForm_Bratu_IFunction), PETIGA_SLOT_IFUNCTION, PETIGA_FORM_BRATU, 1, 0},
       {FN(IGADeviceForm_Bratu_IJacobian), PETIGA_SLOT_IJACOBIAN, PETIGA_FORM_BRATU, 1, 0},
+      {FN(IGADeviceForm_Nitsche_System), PETIGA_SLOT_SYSTEM, PETIGA_FORM_NITSCHE, 0, 0},
+      {FN(IGADeviceForm_SNES2D_Function), PETIGA_SLOT_FUNCTION, PETIGA_FORM_SNES2D, 0, 0},
+      {FN(IGADeviceForm_SNES2D_Jacobian), PETIGA_SLOT_JACOBIAN, PETIGA_FORM_SNES2D, 0, 0},
+      {FN(IGADeviceForm_PatternFormation_IEFunction), PETIGA_SLOT_IEFUNCTION, PETIGA_FORM_PATTERNFORMATION, 9, 2},
+      {FN(IGADeviceForm_PatternFormation_IEJacobian), PETIGA_SLOT_IEJACOBIAN, PETIGA_FORM_PATTERNFORMATION, 9, 2},
+      {FN(IGADeviceForm_ElasticRod_I2Function), PETIGA_SLOT_I2FUNCTION, PETIGA_FORM_ELASTICROD, 2, 0},
+      {FN(IGADeviceForm_ElasticRod_I2Jacobian), PETIGA_SLOT_I2JACOBIAN, PETIGA_FORM_ELASTICROD, 2, 0},
+      {FN(IGADeviceForm_Bratu_RHSFunction), PETIGA_SLOT_RHSFUNCTION, PETIGA_FORM_BRATU, 1, 0},
+      {FN(IGADeviceForm_Bratu_RHSJacobian), PETIGA_SLOT_RHSJACOBIAN, PETIGA_FORM_BRATU, 1, 0},
   };
   for (const auto& e : table) if (e.fn == fn && e.slot == slot) return &e;
   return nullptr;
@@ -307,8 +317,13 @@ PetscErrorCode set_form(IGA g, int slot, const void* fn, void* ctx) {
   if (fe->nprm && !ctx) return fail(PETSC_ERR_ARG_NULL, "IGASetForm*: this form needs its AppCtx");   // nothing committed yet
   s.form = fe->form; s.nprm = fe->nprm; s.dirty = true;
   memset(s.prm, 0, sizeof(s.prm));
-  for (int k = 0; k < fe->nprm; k++) s.prm[k] = ((const double*)ctx)[k];
-  if (fe->swap01) std::swap(s.prm[0], s.prm[1]);   // demo/Elasticity.c AppCtx is {mu, lambda}
+  if (fe->swap01 == 2) {   // {PetscBool flag; PetscReal ...}: the flag occupies the first 8-byte slot of the struct
+    s.prm[0] = (double)(*(const int*)ctx != 0);
+    for (int k = 1; k < fe->nprm; k++) s.prm[k] = ((const double*)ctx)[k];
+  } else {
+    for (int k = 0; k < fe->nprm; k++) s.prm[k] = ((const double*)ctx)[k];
+    if (fe->swap01 == 1) std::swap(s.prm[0], s.prm[1]);   // demo/Elasticity.c AppCtx is {mu, lambda}
+  }
   return 0;
 }
 
@@ -337,6 +352,12 @@ PetscErrorCode IGADeviceScalar_CahnHilliard2D_Stats(IGAPoint, const PetscScalar*
 PetscErrorCode IGADeviceExact_ErrNormTest(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 PetscErrorCode IGADeviceExact_L2Projection(IGAPoint, PetscInt, PetscScalar*, void*) { return host_sentinel(); }
 SENTF(IGADeviceForm_Bratu_Function) SENTF(IGADeviceForm_Bratu_Jacobian) SENTI(IGADeviceForm_Bratu_IFunction) SENTI(IGADeviceForm_Bratu_IJacobian)
+SENT4(IGADeviceForm_Nitsche_System) SENTF(IGADeviceForm_SNES2D_Function) SENTF(IGADeviceForm_SNES2D_Jacobian)
+#define SENT3V(name) PetscErrorCode name(IGAPoint, PetscReal, const PetscScalar*, PetscReal, const PetscScalar*, PetscReal, const PetscScalar*, PetscScalar*, void*) { return host_sentinel(); }
+#define SENTR(name) PetscErrorCode name(IGAPoint, PetscReal, const PetscScalar*, PetscScalar*, void*) { return host_sentinel(); }
+SENT3V(IGADeviceForm_PatternFormation_IEFunction) SENT3V(IGADeviceForm_PatternFormation_IEJacobian)
+SENT3V(IGADeviceForm_ElasticRod_I2Function) SENT3V(IGADeviceForm_ElasticRod_I2Jacobian)
+SENTR(IGADeviceForm_Bratu_RHSFunction) SENTR(IGADeviceForm_Bratu_RHSJacobian)
 
 PetscErrorCode IGA_Partition(PetscInt size, PetscInt rank, PetscInt dim, const PetscInt N[], PetscInt n[], PetscInt i[]) {
   if (size < 1) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Number of partitions must be positive");
@@ -713,6 +734,13 @@ PetscErrorCode IGASetFormJacobian(IGA g, IGAFormJacobian f, void* ctx) { return 
 PetscErrorCode IGASetFormIFunction(IGA g, IGAFormIFunction f, void* ctx) { return set_form(g, PETIGA_SLOT_IFUNCTION, (const void*)f, ctx); }
 PetscErrorCode IGASetFormIJacobian(IGA g, IGAFormIJacobian f, void* ctx) { return set_form(g, PETIGA_SLOT_IJACOBIAN, (const void*)f, ctx); }
 
+PetscErrorCode IGASetFormI2Function(IGA g, IGAFormI2Function f, void* ctx) { return set_form(g, PETIGA_SLOT_I2FUNCTION, (const void*)f, ctx); }
+PetscErrorCode IGASetFormI2Jacobian(IGA g, IGAFormI2Jacobian f, void* ctx) { return set_form(g, PETIGA_SLOT_I2JACOBIAN, (const void*)f, ctx); }
+PetscErrorCode IGASetFormIEFunction(IGA g, IGAFormIEFunction f, void* ctx) { return set_form(g, PETIGA_SLOT_IEFUNCTION, (const void*)f, ctx); }
+PetscErrorCode IGASetFormIEJacobian(IGA g, IGAFormIEJacobian f, void* ctx) { return set_form(g, PETIGA_SLOT_IEJACOBIAN, (const void*)f, ctx); }
+PetscErrorCode IGASetFormRHSFunction(IGA g, IGAFormRHSFunction f, void* ctx) { return set_form(g, PETIGA_SLOT_RHSFUNCTION, (const void*)f, ctx); }
+PetscErrorCode IGASetFormRHSJacobian(IGA g, IGAFormRHSJacobian f, void* ctx) { return set_form(g, PETIGA_SLOT_RHSJACOBIAN, (const void*)f, ctx); }
+
 PetscErrorCode IGACreateMat(IGA g, Mat* mat) {
   if (PetscErrorCode e = check(g)) return e;
   if (!mat) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
@@ -779,14 +807,15 @@ PetscErrorCode VecGetArrayHost(Vec v, PetscScalar* out) { if (!v || !out) return
 PetscErrorCode VecSetArrayHost(Vec v, const PetscScalar* in) { if (!v || !in) return fail(PETSC_ERR_ARG_NULL, "Null"); if (PetscErrorCode e = check_owner(v, nullptr, "Vec")) return e; if (v->iga->plan) petiga_cuda_plan_activate(v->iga->plan); return from_cuda(petiga_cuda_memcpy_h2d(v->d, in, (size_t)v->n * sizeof(double))); }
 PetscErrorCode VecGetArrayDevice(Vec v, PetscScalar** d) { if (!v || !d) return fail(PETSC_ERR_ARG_NULL, "Null"); *d = v->d; return 0; }
 
-static PetscErrorCode run(IGA g, int slot, PetscReal a, Vec V, PetscReal t, Vec U, Mat A, Vec B) {
+static PetscErrorCode run(IGA g, int slot, PetscReal a, Vec V, PetscReal t, Vec U, Mat A, Vec B, PetscReal a2 = 0, Vec W = nullptr, PetscReal t0 = 0) {
   if (PetscErrorCode e = check(g)) return e;
   if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");                     // IGACheckSetUp
   if (g->slots[slot].form < 0) return fail(PETSC_ERR_USER, "Must call IGASetForm*() first");
   if (PetscErrorCode e = ensure_plan(g)) return e;
   if (A) if (PetscErrorCode e = check_owner(A, g, "Mat")) return e;
-  for (Vec x : {V, U, B}) if (x) if (PetscErrorCode e = check_owner(x, g, "Vec")) return e;
-  int rc = petiga_cuda_compute(g->plan, slot, A ? A->baij : 0, a, V ? V->d : nullptr, t, U ? U->d : nullptr, A ? A->d_values : nullptr, B ? B->d : nullptr);
+  for (Vec x : {V, U, B, W}) if (x) if (PetscErrorCode e = check_owner(x, g, "Vec")) return e;
+  int rc = petiga_cuda_compute_ext(g->plan, slot, A ? A->baij : 0, a, V ? V->d : nullptr, t, U ? U->d : nullptr, a2, W ? W->d : nullptr, t0,
+                                   A ? A->d_values : nullptr, B ? B->d : nullptr);
   if (rc) return from_cuda(rc);
   if (g->async) return 0;                          // device-resident hand-off: ordered on the IGA's stream, no host wait
   return from_cuda(petiga_cuda_finish(g->plan));   // Mat/VecAssemblyEnd: fully assembled on return
@@ -802,6 +831,14 @@ PetscErrorCode IGAComputeFunction(IGA g, Vec U, Vec F) { if (!U || !F) return fa
 PetscErrorCode IGAComputeJacobian(IGA g, Vec U, Mat J) { if (!U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_JACOBIAN, 0, nullptr, 0, U, J, nullptr); }
 PetscErrorCode IGAComputeIFunction(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, Vec F) { if (!V || !U || !F) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_IFUNCTION, a, V, t, U, nullptr, F); }
 PetscErrorCode IGAComputeIJacobian(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, Mat J) { if (!V || !U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_IJACOBIAN, a, V, t, U, J, nullptr); }
+
+// src/petigats.c:182-477 and src/petigats2.c:23-175: same skeleton, a third vector (U0 / A) and a second time / shift
+PetscErrorCode IGAComputeIEFunction(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, PetscReal t0, Vec U0, Vec F) { if (!V || !U || !U0 || !F) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_IEFUNCTION, a, V, t, U, nullptr, F, 0, U0, t0); }
+PetscErrorCode IGAComputeIEJacobian(IGA g, PetscReal a, Vec V, PetscReal t, Vec U, PetscReal t0, Vec U0, Mat J) { if (!V || !U || !U0 || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_IEJACOBIAN, a, V, t, U, J, nullptr, 0, U0, t0); }
+PetscErrorCode IGAComputeRHSFunction(IGA g, PetscReal t, Vec U, Vec F) { if (!U || !F) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_RHSFUNCTION, 0, nullptr, t, U, nullptr, F); }
+PetscErrorCode IGAComputeRHSJacobian(IGA g, PetscReal t, Vec U, Mat J) { if (!U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_RHSJACOBIAN, 0, nullptr, t, U, J, nullptr); }
+PetscErrorCode IGAComputeI2Function(IGA g, PetscReal a, Vec A, PetscReal v, Vec V, PetscReal t, Vec U, Vec F) { if (!A || !V || !U || !F) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_I2FUNCTION, a, V, t, U, nullptr, F, v, A, 0); }
+PetscErrorCode IGAComputeI2Jacobian(IGA g, PetscReal a, Vec A, PetscReal v, Vec V, PetscReal t, Vec U, Mat J) { if (!A || !V || !U || !J) return fail(PETSC_ERR_ARG_NULL, "Null Vec/Mat"); return run(g, PETIGA_SLOT_I2JACOBIAN, a, V, t, U, J, nullptr, v, A, 0); }
 
 // src/petigacomp.c:35-96
 PetscErrorCode IGAComputeScalar(IGA g, Vec vecU, PetscInt n, PetscScalar S[], IGAFormScalar Scalar, void* ctx) {

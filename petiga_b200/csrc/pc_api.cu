@@ -1,4 +1,6 @@
 // pc_api.cu -- extern "C" entry points of libpetiga_cuda (see include/petiga_cuda.h).
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -8,6 +10,32 @@
 #include "pc_plan.h"
 
 namespace pc {
+
+// NVTX ranges around the driver bodies (tracing).  libnvToolsExt is loaded lazily with dlopen so that the library has
+// no link-time dependency on it; without it the ranges are no-ops.
+namespace {
+typedef int (*nvtx_push_t)(const char*);
+typedef int (*nvtx_pop_t)(void);
+nvtx_push_t g_nvtx_push = nullptr;
+nvtx_pop_t g_nvtx_pop = nullptr;
+int g_nvtx_state = 0;   // 0 untried, 1 loaded, -1 unavailable
+const char* const kSlotNames[PETIGA_NSLOTS] = {"IGAComputeVector", "IGAComputeMatrix", "IGAComputeSystem", "IGAComputeFunction", "IGAComputeJacobian",
+                                               "IGAComputeIFunction", "IGAComputeIJacobian", "IGAComputeIEFunction", "IGAComputeIEJacobian",
+                                               "IGAComputeRHSFunction", "IGAComputeRHSJacobian", "IGAComputeI2Function", "IGAComputeI2Jacobian"};
+void nvtx_init() {
+  if (g_nvtx_state) return;
+  g_nvtx_state = -1;
+  for (const char* n : {"libnvToolsExt.so.1", "libnvToolsExt.so"}) {
+    void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) continue;
+    g_nvtx_push = (nvtx_push_t)dlsym(h, "nvtxRangePushA");
+    g_nvtx_pop = (nvtx_pop_t)dlsym(h, "nvtxRangePop");
+    if (g_nvtx_push && g_nvtx_pop) { g_nvtx_state = 1; return; }
+  }
+}
+}  // namespace
+void nvtx_push(int slot) { nvtx_init(); if (g_nvtx_state == 1) g_nvtx_push(kSlotNames[slot]); }
+void nvtx_pop() { if (g_nvtx_state == 1) g_nvtx_pop(); }
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -285,6 +313,7 @@ int petiga_cuda_plan_create(petiga_cuda_plan** plan, const petiga_cuda_space* sp
     if ((rc = upload<double>(P, nullptr, nl, &P->d_rhs_loc))) return bail(rc);
     if ((rc = upload<double>(P, nullptr, nl, &P->d_U_loc))) return bail(rc);
     if ((rc = upload<double>(P, nullptr, nl, &P->d_V_loc))) return bail(rc);
+    if ((rc = upload<double>(P, nullptr, nl, &P->d_W_loc))) return bail(rc);
     std::vector<int> rows;
     std::vector<int64_t> offs;      // prefix sum of the row lengths inside each peer's slab (the sender packs rows back to back)
     P->recv_row_off.clear();
@@ -324,7 +353,7 @@ int petiga_cuda_set_option(petiga_cuda_plan* P, const char* name, double value) 
   if (!P || !name) return PETIGA_CUDA_ERR_ARG;
   if (!strcmp(name, "path")) { int v = (int)value; if (v < 0 || v > 2) return PETIGA_CUDA_ERR_ARG; P->path = v; return 0; }
   if (!strcmp(name, "scatter")) { P->scatter = (int)value; return 0; }
-  if (!strcmp(name, "quad_impl")) { P->quad_impl = (int)value; return 0; }
+  if (!strcmp(name, "quad_impl")) { int v = (int)value; if (v < -1 || v > 3) return PETIGA_CUDA_ERR_ARG; P->quad_impl = v; return 0; }
   set_error(std::string("unknown option ") + name);
   return PETIGA_CUDA_ERR_ARG;
 }
@@ -440,7 +469,7 @@ int petiga_cuda_form_select(petiga_cuda_plan* P, int slot, int form_id, const do
     P->config_version++;
     return 0;
   }
-  if (!P || slot < 0 || slot >= PETIGA_NSLOTS || form_id < 0 || form_id >= PETIGA_NFORMS || nparams < 0 || nparams > 8) {
+  if (!P || slot < 0 || slot >= PETIGA_NSLOTS || form_id < 0 || form_id >= PETIGA_NFORMS || nparams < 0 || nparams > kMaxPrm) {
     set_error("form_select: bad slot / form / nparams");
     return PETIGA_CUDA_ERR_ARG;
   }
@@ -524,37 +553,43 @@ static int ensure(double** buf, size_t* cap, size_t n) {
 
 int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, const double* V, double t, const double* U,
                         double* values, double* rhs) {
+  return petiga_cuda_compute_ext(P, slot, block, shift, V, t, U, 0.0, nullptr, 0.0, values, rhs);
+}
+
+int petiga_cuda_compute_ext(petiga_cuda_plan* P, int slot, int block, double shift, const double* V, double t, const double* U,
+                            double shift2, const double* W, double t0, double* values, double* rhs) {
   if (!P || slot < 0 || slot >= PETIGA_NSLOTS || (block != 0 && block != 1)) return PETIGA_CUDA_ERR_ARG;
   const Layout& L = P->L;
   const int form = P->slots[slot].form;
   if (form < 0) { set_error("compute: no form selected for this slot (IGACheckFormOp)"); return PETIGA_CUDA_ERR_ORDER; }
   FormInfo fi = form_info(form, slot, L.dim, L.dof);
   if (!fi.valid) return PETIGA_CUDA_ERR_SUP;
-  const bool want_mat = (slot == PETIGA_SLOT_MATRIX || slot == PETIGA_SLOT_SYSTEM || slot == PETIGA_SLOT_JACOBIAN || slot == PETIGA_SLOT_IJACOBIAN);
-  const bool want_vec = (slot == PETIGA_SLOT_VECTOR || slot == PETIGA_SLOT_SYSTEM || slot == PETIGA_SLOT_FUNCTION || slot == PETIGA_SLOT_IFUNCTION);
-  const bool state = (slot >= PETIGA_SLOT_FUNCTION);
-  const bool transient = (slot == PETIGA_SLOT_IFUNCTION || slot == PETIGA_SLOT_IJACOBIAN);
+  const bool want_mat = slot_has_mat(slot), want_vec = slot_has_vec(slot);
+  const bool state = slot_has_state(slot), has_v = slot_has_v(slot), has_w = slot_has_w(slot);
   if (want_mat && !values) { set_error("compute: values == NULL"); return PETIGA_CUDA_ERR_ARG; }
   if (want_vec && !rhs) { set_error("compute: rhs == NULL"); return PETIGA_CUDA_ERR_ARG; }
   if (state && !U) { set_error("compute: U == NULL"); return PETIGA_CUDA_ERR_ARG; }
-  if (transient && !V) { set_error("compute: V == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (has_v && !V) { set_error("compute: V == NULL"); return PETIGA_CUDA_ERR_ARG; }
+  if (has_w && !W) { set_error("compute: the third vector (U0 / A) == NULL"); return PETIGA_CUDA_ERR_ARG; }
   if (fi.order > P->order) { set_error("compute: form reads derivatives above IGASetOrder"); return PETIGA_CUDA_ERR_ARG; }
   PC_CUDA(cudaSetDevice(P->device));
   const int bs2 = L.dof * L.dof;
   const size_t nval = (size_t)L.nnz_own * bs2, nvec = (size_t)L.nown * L.dof;
   const bool multi = L.nranks > 1;
+  nvtx_push(slot);
 
   // boundary-integral pass (IGASetBoundaryForm): which faces are visited, and does the form have a face term?
   bool any_visit = false;
   for (int d = 0; d < L.dim; d++) for (int s = 0; s < 2; s++) if (P->visit[d][s] && !L.ax[d].periodic) any_visit = true;
-  if (any_visit && !form_has_boundary_term(form)) { set_error("compute: a face is enabled with IGASetBoundaryForm but this built-in form has no boundary term"); return PETIGA_CUDA_ERR_SUP; }
-  const bool bnd_pass = any_visit && want_vec;
+  if (any_visit && !(fi.bnd_mat || fi.bnd_vec)) { nvtx_pop(); set_error("compute: a face is enabled with IGASetBoundaryForm but this built-in form has no boundary term"); return PETIGA_CUDA_ERR_SUP; }
+  const bool bnd_pass = any_visit && ((want_vec && fi.bnd_vec) || (want_mat && fi.bnd_mat));
   // path selection
   const bool kron_ok = kron_applicable(P, slot, form) && !bnd_pass;
-  if (P->path == PETIGA_PATH_KRONECKER && !kron_ok) { set_error("compute: separable path not applicable (geometry, state or non-separable form)"); return PETIGA_CUDA_ERR_SUP; }
+  if (P->path == PETIGA_PATH_KRONECKER && !kron_ok) { nvtx_pop(); set_error("compute: separable path not applicable (geometry, state or non-separable form)"); return PETIGA_CUDA_ERR_SUP; }
   const bool use_kron = kron_ok && P->path != PETIGA_PATH_QUADRATURE;
   P->last_path = use_kron ? PETIGA_PATH_KRONECKER : PETIGA_PATH_QUADRATURE;
   P->last_flops = 0;
+  struct Pop { ~Pop() { nvtx_pop(); } } pop_on_exit;
 
   cudaEventRecord(P->ev0, P->stream);
   bool quad_mat = want_mat;   // does the quadrature kernel still have to produce the matrix?
@@ -577,16 +612,16 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
     if (want_vec) { rhs_k = P->d_rhs_loc; PC_CUDA(cudaMemsetAsync(rhs_k, 0, (size_t)L.nloc * L.dof * sizeof(double), P->stream)); }
   } else if (want_vec) PC_CUDA(cudaMemsetAsync(rhs, 0, nvec * sizeof(double), P->stream));
 
-  // IGAGetLocalVecArray: G2L halo of the state (petigavec.c:256-269)
-  const double *U_k = U, *V_k = V;
+  // IGAGetLocalVecArray: G2L halo of the state vectors (petigavec.c:256-269)
+  const double *U_k = U, *V_k = V, *W_k = W;
   if (multi && state) {
     int rc = halo_state(P, U, P->d_U_loc);
     if (rc) return rc;
     U_k = P->d_U_loc;
-    if (transient) { rc = halo_state(P, V, P->d_V_loc); if (rc) return rc; V_k = P->d_V_loc; }
+    if (has_v) { rc = halo_state(P, V, P->d_V_loc); if (rc) return rc; V_k = P->d_V_loc; }
+    if (has_w) { rc = halo_state(P, W, P->d_W_loc); if (rc) return rc; W_k = P->d_W_loc; }
   }
 
-  if (P->d_X && fi.order > 1) { set_error("compute: second derivatives on a mapped geometry are not available on the device path yet"); return PETIGA_CUDA_ERR_SUP; }
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   for (int d = 0; d < 3; d++) kp.ax[d] = P->dax[d];
@@ -595,7 +630,13 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   kp.nown = L.nown; kp.nnz_own = L.nnz_own;
   kp.localrow = P->d_localrow; kp.rowbase = P->d_rowbase;
   kp.values = values; kp.ghost_values = P->d_ghost_values; kp.rhs = rhs_k;
-  kp.U = state ? U_k : nullptr; kp.V = transient ? V_k : nullptr;
+  kp.U = state ? U_k : nullptr; kp.V = has_v ? V_k : nullptr; kp.Wv = has_w ? W_k : nullptr;
+  kp.shift2 = shift2; kp.t0 = t0;
+  kp.face_axis = kp.face_side = -1;
+  for (int d = 0; d < 3; d++) {
+    kp.maxdeg = std::max(kp.maxdeg, d < L.dim ? L.ax[d].p : 0);
+    for (int s2 = 0; s2 < 2; s2++) { kp.bnd_value[d][s2] = P->d_bnd_value[d][s2]; kp.bnd_point[d][s2] = P->bnd_point[d][s2]; }
+  }
   kp.X = P->d_X; kp.Wt = P->d_W; kp.fixtable = P->d_fixtable;
   kp.any_bc = 0;
   const bool apply_bc = (slot != PETIGA_SLOT_VECTOR && slot != PETIGA_SLOT_MATRIX);   // IGAComputeVector/Matrix never fix (petigaksp.c:33-139)
@@ -654,17 +695,41 @@ int petiga_cuda_compute(petiga_cuda_plan* P, int slot, int block, double shift, 
   memcpy(kp.prm, P->slots[slot].prm, sizeof(kp.prm));
   kp.shift = shift; kp.t = t;
   kp.noscatter = (P->scatter == 99);
-  // kernel choice (measured, profiles/r1_configs_1gpu.jsonl): the sum-factorised kernel wins on large elements (3-D, p >= 2:
-  // 6x at cfg 2), the pair-loop kernel on small ones where per-element set-up dominates (5x at cfg 5, 2-D p=2)
-  int impl = P->quad_impl;
-  if (impl < 0) impl = (L.dim == 3 && L.ax[0].p >= 2) ? 0 : 1;
-  int rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
-  if (rc == PETIGA_CUDA_ERR_SUP && P->quad_impl < 0) rc = impl == 1 ? launch_quadrature_sf(P, kp) : launch_quadrature(P, kp);
+  // kernel choice (measured, profiles/): the sum-factorised kernels win on large elements (3-D, p >= 2), the pair-loop kernel on
+  // small ones where per-element set-up dominates (2-D p=2).  What the tuned kernels do not instantiate -- mixed degrees per
+  // axis, degree > 4, dof > 3, second derivatives on mapped / NURBS geometry, the IE/RHS/I2 drivers -- runs the generic kernel.
+  const bool need_gen = slot >= PETIGA_SLOT_IEFUNCTION || (P->d_X && fi.order > 1) || P->quad_impl == 2;
+  int impl = P->quad_impl, rc;
+  if (need_gen) { impl = 2; rc = launch_quadrature_gen(P, kp); }
+  else {
+    if (impl < 0) impl = (L.dim == 3 && L.ax[0].p >= 2) ? 0 : 1;
+    rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+    if (rc == PETIGA_CUDA_ERR_SUP && P->quad_impl < 0) {
+      impl = 1 - impl;
+      rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+      if (rc == PETIGA_CUDA_ERR_SUP) { impl = 2; rc = launch_quadrature_gen(P, kp); }
+    }
+  }
   if (rc) return rc;
   P->last_impl = impl;
-  if (bnd_pass) {   // face terms go into the same (unified local) vector, before the ghost-row exchange
-    rc = launch_boundary_pass(P, slot, form, P->slots[slot].prm, rhs_k, apply_bc && P->has_bc);
-    if (rc) return rc;
+  if (bnd_pass) {   // face terms go into the same (unified local) arrays, before the ghost-row exchange
+    if (fi.bnd_mat) {   // full forms on the visited faces (matrix + vector terms): the generic kernel in face mode, one launch per face
+      for (int d = 0; d < L.dim; d++)
+        for (int s = 0; s < 2; s++) {
+          if (!P->visit[d][s] || L.ax[d].periodic) continue;
+          const int face_e = s ? L.ax[d].nel - 1 : 0;
+          if (face_e < L.ax[d].es || face_e >= L.ax[d].es + L.ax[d].ew) continue;
+          if (!P->d_bnd_value[d][s]) { set_error("compute: boundary tables not set (petiga_cuda_set_boundary_tables)"); return PETIGA_CUDA_ERR_ORDER; }
+          KParams kf = kp;
+          kf.face_axis = d; kf.face_side = s;
+          kf.mc1 = want_mat ? fi.mc1 : fi.mc0;
+          rc = launch_quadrature_gen(P, kf);
+          if (rc) return rc;
+        }
+    } else {
+      rc = launch_boundary_pass(P, slot, form, P->slots[slot].prm, rhs_k, apply_bc && P->has_bc);
+      if (rc) return rc;
+    }
   }
   cudaEventRecord(P->ev1, P->stream);
   if (multi) {

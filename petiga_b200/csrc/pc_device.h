@@ -43,6 +43,12 @@ struct KParams {
   double* rhs;                     // [nloc*dof] unified local vector (owned first)
   const double* U;                 // [nloc*dof] unified local state (owned first) or NULL
   const double* V;
+  const double* Wv;                // third state vector: U0 of the IE drivers / A of the I2 drivers, or NULL
+  double shift2, t0;               // second shift (I2: shiftV) / second time (IE: t0)
+  int face_axis, face_side;        // generic kernel in face mode: the visited face (IGAElementNextForm, petigaelem.c:427-447), else -1
+  const double* bnd_value[3][2];   // IGABasis.bnd_value of every axis end ([p+1][5]) for the face mode
+  double bnd_point[3][2];
+  int maxdeg;
   const double* X;                 // geometry [ghost box][dim] or NULL
   const double* Wt;                // rational weights [ghost box] or NULL
   const double* fixtable;          // [ghost box][dof] or NULL
@@ -52,7 +58,7 @@ struct KParams {
   int form, slot, block;           // block: 1 = BAIJ value layout, 0 = AIJ
   int mc0, mc1, vc0, vc1, per_qp, needs_x, needs_state;
   int c0, c1;                      // tabulated component range (union)
-  double prm[8];
+  double prm[kMaxPrm];
   double shift, t;
   int qc;                          // quadrature points per chunk
   int epb;                         // elements per block

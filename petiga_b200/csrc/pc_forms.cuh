@@ -18,7 +18,30 @@
 namespace pc {
 
 constexpr int kMaxComp = 5;   // N, 3 derivatives, Laplacian
-constexpr int kMaxDof = 4;
+constexpr int kMaxDof = 8;    // test/IGACreate.c sweeps dof 1..8 (test/makefile:23-40)
+constexpr int kMaxPrm = 12;   // reals of the largest AppCtx (demo/PatternFormation.c:14-24: flag + 8)
+
+// which IGACompute* a slot stands for (include/petiga.h:837-851, src/petigats.c:182-477, src/petigats2.c:23-175)
+__host__ __device__ inline bool slot_has_mat(int s) {
+  return s == PETIGA_SLOT_MATRIX || s == PETIGA_SLOT_SYSTEM || s == PETIGA_SLOT_JACOBIAN || s == PETIGA_SLOT_IJACOBIAN ||
+         s == PETIGA_SLOT_IEJACOBIAN || s == PETIGA_SLOT_RHSJACOBIAN || s == PETIGA_SLOT_I2JACOBIAN;
+}
+__host__ __device__ inline bool slot_has_vec(int s) {
+  return s == PETIGA_SLOT_VECTOR || s == PETIGA_SLOT_SYSTEM || s == PETIGA_SLOT_FUNCTION || s == PETIGA_SLOT_IFUNCTION ||
+         s == PETIGA_SLOT_IEFUNCTION || s == PETIGA_SLOT_RHSFUNCTION || s == PETIGA_SLOT_I2FUNCTION;
+}
+__host__ __device__ inline bool slot_has_state(int s) { return s >= PETIGA_SLOT_FUNCTION; }            // reads U
+__host__ __device__ inline bool slot_has_w(int s) {                                                     // third vector: U0 (IE) / A (I2)
+  return s == PETIGA_SLOT_IEFUNCTION || s == PETIGA_SLOT_IEJACOBIAN || s == PETIGA_SLOT_I2FUNCTION || s == PETIGA_SLOT_I2JACOBIAN;
+}
+__host__ __device__ inline bool slot_has_v(int s) { return s == PETIGA_SLOT_IFUNCTION || s == PETIGA_SLOT_IJACOBIAN || slot_has_w(s); }
+__host__ __device__ inline bool slot_is_i2(int s) { return s == PETIGA_SLOT_I2FUNCTION || s == PETIGA_SLOT_I2JACOBIAN; }
+// element fix-up applied after the quadrature loop: 0 none (IGAComputeVector/Matrix), 1 FixSystem, 2 FixFunction, 3 FixJacobian
+__host__ __device__ inline int slot_fix_kind(int s) {
+  if (s == PETIGA_SLOT_SYSTEM) return 1;
+  if (!slot_has_state(s)) return 0;
+  return slot_has_vec(s) ? 2 : 3;
+}
 
 // static description of a (form, slot) pair: which Psi components the matrix / vector parts read
 struct FormInfo {
@@ -31,10 +54,11 @@ struct FormInfo {
   int order;          // highest derivative read (0, 1 or 2)
   int constant_f;     // vector coefficient is a constant (eligible for the separable path)
   int mat_const;      // matrix coefficient tensor does not depend on the point
+  int bnd_mat, bnd_vec;   // the callback has a p->atboundary branch that adds matrix / vector terms on visited faces
 };
 
 __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int dof) {
-  FormInfo f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  FormInfo f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool lin = (slot == PETIGA_SLOT_VECTOR || slot == PETIGA_SLOT_MATRIX || slot == PETIGA_SLOT_SYSTEM);
   const bool fun = (slot == PETIGA_SLOT_FUNCTION || slot == PETIGA_SLOT_IFUNCTION);
   const bool jac = (slot == PETIGA_SLOT_JACOBIAN || slot == PETIGA_SLOT_IJACOBIAN);
@@ -89,11 +113,32 @@ __host__ __device__ inline FormInfo form_info(int form, int slot, int dim, int d
       break;
     case PETIGA_FORM_BRATU:
       if (dof != 1) break;
-      if (fun) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
-      if (jac) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      if (fun || slot == PETIGA_SLOT_RHSFUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      if (jac || slot == PETIGA_SLOT_RHSJACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      break;
+    case PETIGA_FORM_SNES2D:            // test/Test_SNES_2D.c:12-72 (dof 4, dim 2)
+      if (dim != 2 || dof != 4) break;
+      if (slot == PETIGA_SLOT_FUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 3; f.per_qp = 1; f.needs_state = 1; f.needs_x = 1; f.order = 1; }
+      if (slot == PETIGA_SLOT_JACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 3; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      break;
+    case PETIGA_FORM_PATTERNFORMATION:  // demo/PatternFormation.c:26-141 (dof 2, dim 2)
+      if (dim != 2 || dof != 2) break;
+      if (slot == PETIGA_SLOT_IEFUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 3; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      if (slot == PETIGA_SLOT_IEJACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 3; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      break;
+    case PETIGA_FORM_ELASTICROD:        // demo/ElasticRodFJ.F90
+      if (dof != 1) break;
+      if (slot == PETIGA_SLOT_I2FUNCTION) { f.valid = 1; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_state = 1; f.order = 1; }
+      if (slot == PETIGA_SLOT_I2JACOBIAN) { f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.order = 1; }
+      break;
+    case PETIGA_FORM_NITSCHE:           // demo/NitscheMethod.c:70-119: interior Poisson (f = -2 dim) + face terms
+      if (dof != 1 || slot != PETIGA_SLOT_SYSTEM) break;
+      f.valid = 1; f.mc0 = 0; f.mc1 = 1 + dim; f.vc0 = 0; f.vc1 = 1 + dim; f.per_qp = 1; f.needs_x = 1; f.order = 1; f.bnd_mat = 1; f.bnd_vec = 1;
       break;
   }
-  f.mat_const = !f.per_qp || form == PETIGA_FORM_L2PROJECTION || form == PETIGA_FORM_NEUMANN || form == PETIGA_FORM_CONVTEST;
+  if (form == PETIGA_FORM_BOUNDARYINTEGRAL && f.valid) f.bnd_vec = 1;
+  f.mat_const = !f.per_qp || form == PETIGA_FORM_L2PROJECTION || form == PETIGA_FORM_NEUMANN || form == PETIGA_FORM_CONVTEST ||
+                form == PETIGA_FORM_NITSCHE;
   if (slot == PETIGA_SLOT_VECTOR) { f.mc0 = f.mc1 = 0; }
   if (slot == PETIGA_SLOT_MATRIX) { f.vc0 = f.vc1 = 0; }
   return f;
@@ -129,15 +174,21 @@ struct QPoint {
   double v[kMaxDof];    // IGAPointFormValue(V)
   double gu[kMaxDof][3];// IGAPointFormGrad(U)
   double d2u[kMaxDof];  // IGAPointFormDel2(U)
+  double w[kMaxDof];    // IGAPointFormValue of the third vector: U0 (IE drivers) or A (I2 drivers)
+  // boundary-integral pass (p->atboundary, include/petiga.h:645-647,668): only the generic kernel's face mode sets these
+  int atboundary;
+  double normal[3];     // outward unit normal (IGA_GetNormal, src/petigaval.F90:45-99)
+  double hn;            // demo/NitscheMethod.c:58-67 NormalMeshSize: 2 / |G^T n|, G = IGAPointFormInvGradGeomMap
+  int maxdeg;           // max axis degree (Degree(), :48-56)
 };
 
 // Fill the coefficient tensors of one quadrature point.
 //   C : [DOF][DOF][NA][NA]  (NA = mc1-mc0), index ((i*DOF+j)*NA+al)*NA+be, components relative to mc0
 //   fv: [DOF][NV]           (NV = vc1-vc0), index i*NV+al, components relative to vc0
 // Both are pre-zeroed by the caller.
-template <int DIM, int DOF>
-__host__ __device__ inline void form_coefficients(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
-                                         int NA, int NV, double* C, double* fv) {
+template <int DIM>
+__host__ __device__ __forceinline__ void form_coefficients_rt(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
+                                                              const int DOF, int NA, int NV, double* C, double* fv) {
   (void)t;
   switch (form) {
     case PETIGA_FORM_POISSON:   // demo/Poisson3D.c:18,20 ; residual/tangent of the same problem for SNES slots
@@ -227,12 +278,92 @@ __host__ __device__ inline void form_coefficients(int form, int slot, const doub
     }
     case PETIGA_FORM_BRATU: {   // demo/BratuFJ.F90:22-62 (Function), :64-114 (Jacobian), :118-150 (IFunction), IJacobian
       const double lam = prm[0], eu = exp(q.u[0]);
+      if (slot == PETIGA_SLOT_RHSFUNCTION || slot == PETIGA_SLOT_RHSJACOBIAN) {
+        // explicit form u_t = lap u + lambda exp(u): G_a = -grad N_a . grad u + N_a lambda exp(u) (no reference demo registers an
+        // RHSFunction; this exercises IGAComputeRHSFunction/RHSJacobian, src/petigats.c:357-477)
+        if (fv && NV) { fv[0] = lam * eu; for (int d = 0; d < DIM; d++) fv[1 + d] = -q.gu[0][d]; }
+        if (C && NA) { C[0] = lam * eu; for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = -1.0; }
+        break;
+      }
       const bool tr = (slot == PETIGA_SLOT_IFUNCTION || slot == PETIGA_SLOT_IJACOBIAN);
       if (fv && NV) { fv[0] = (tr ? q.v[0] : 0.0) - lam * eu; for (int d = 0; d < DIM; d++) fv[1 + d] = q.gu[0][d]; }
       if (C && NA) { C[0] = (tr ? shift : 0.0) - lam * eu; for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = 1.0; }
       break;
     }
+    case PETIGA_FORM_SNES2D: {   // test/Test_SNES_2D.c:12-72: L2 projection of Peaks, Poisson, reaction-diffusion, Bratu
+      if (DIM != 2 || DOF != 4) break;
+      if (fv && NV) {
+        fv[0 * NV + 0] = q.u[0] - l2_function(5, 2, q.x);
+        fv[1 * NV + 0] = -1.0; fv[1 * NV + 1] = q.gu[1][0]; fv[1 * NV + 2] = q.gu[1][1];
+        fv[2 * NV + 0] = q.u[2] - 1.0; fv[2 * NV + 1] = q.gu[2][0]; fv[2 * NV + 2] = q.gu[2][1];
+        fv[3 * NV + 0] = -1.0 * exp(q.u[3]); fv[3 * NV + 1] = q.gu[3][0]; fv[3 * NV + 2] = q.gu[3][1];
+      }
+      if (C && NA) {
+#define CD(i, al, be) C[(((i) * DOF + (i)) * NA + (al)) * NA + (be)]
+        CD(0, 0, 0) = 1.0;
+        CD(1, 1, 1) = 1.0; CD(1, 2, 2) = 1.0;
+        CD(2, 0, 0) = 1.0; CD(2, 1, 1) = 1.0; CD(2, 2, 2) = 1.0;
+        CD(3, 1, 1) = 1.0; CD(3, 2, 2) = 1.0; CD(3, 0, 0) = -1.0 * exp(q.u[3]);
+#undef CD
+      }
+      break;
+    }
+    case PETIGA_FORM_PATTERNFORMATION: {   // demo/PatternFormation.c:26-141; prm = {IMPLICIT, delta, D1, D2, alpha, beta, gamma, tau1, tau2}
+      if (DIM != 2 || DOF != 2) break;
+      const bool impl = prm[0] != 0.0;
+      const double delta = prm[1], D1 = prm[2], D2 = prm[3], alpha = prm[4], beta = prm[5], gamma = prm[6], tau1 = prm[7], tau2 = prm[8];
+      const double u = impl ? q.u[0] : q.w[0], v = impl ? q.u[1] : q.w[1];
+      if (fv && NV) {
+        const double f = alpha * u * (1 - tau1 * v * v) + v * (1 - tau2 * u);
+        const double g = beta * v * (1 + alpha * tau1 / beta * u * v) + u * (gamma + tau2 * v);
+        fv[0 * NV + 0] = q.v[0] - f; fv[0 * NV + 1] = delta * D1 * q.gu[0][0]; fv[0 * NV + 2] = delta * D1 * q.gu[0][1];
+        fv[1 * NV + 0] = q.v[1] - g; fv[1 * NV + 1] = delta * D2 * q.gu[1][0]; fv[1 * NV + 2] = delta * D2 * q.gu[1][1];
+      }
+      if (C && NA) {
+#define CB(i, j, al, be) C[(((i) * DOF + (j)) * NA + (al)) * NA + (be)]
+        CB(0, 0, 0, 0) = shift; CB(0, 0, 1, 1) = delta * D1; CB(0, 0, 2, 2) = delta * D1;
+        CB(1, 1, 0, 0) = shift; CB(1, 1, 1, 1) = delta * D2; CB(1, 1, 2, 2) = delta * D2;
+        if (impl) {
+          const double uu = q.u[0], vv = q.u[1];
+          CB(0, 0, 0, 0) -= alpha * (1 - tau1 * vv * vv) - tau2 * vv;
+          CB(0, 1, 0, 0) -= -2 * alpha * tau1 * uu * vv + (1 - tau2 * uu);
+          CB(1, 0, 0, 0) -= alpha * tau1 * vv * vv + (gamma + tau2 * vv);
+          CB(1, 1, 0, 0) -= (beta + 2 * alpha * tau1 * uu * vv) + tau2 * uu;
+        }
+#undef CB
+      }
+      break;
+    }
+    case PETIGA_FORM_ELASTICROD: {   // demo/ElasticRodFJ.F90:19-95; prm = {rho, E}; shift = shiftA
+      const double rho = prm[0], E = prm[1];
+      if (fv && NV) { fv[0] = rho * q.w[0]; for (int d = 0; d < DIM; d++) fv[1 + d] = E * q.gu[0][d]; }
+      if (C && NA) { C[0] = shift * rho; for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = E; }
+      break;
+    }
+    case PETIGA_FORM_NITSCHE: {   // demo/NitscheMethod.c:70-119
+      if (!q.atboundary) {
+        if (C && NA) for (int d = 0; d < DIM; d++) C[(1 + d) * NA + (1 + d)] = 1.0;
+        if (fv && NV) fv[0] = -2.0 * DIM;
+      } else {
+        double g = 0.0;
+        for (int d = 0; d < DIM; d++) g += q.x[d] * q.x[d];
+        const double alpha = 5 * (q.maxdeg + 1) / q.hn;
+        if (C && NA) {
+          C[0] = alpha;
+          for (int d = 0; d < DIM; d++) { C[0 * NA + (1 + d)] = -q.normal[d]; C[(1 + d) * NA + 0] = -q.normal[d]; }
+        }
+        if (fv && NV) { fv[0] = alpha * g; for (int d = 0; d < DIM; d++) fv[1 + d] = -q.normal[d] * g; }
+      }
+      break;
+    }
   }
+}
+
+// compile-time dof front end of the tuned kernels (same code after inlining)
+template <int DIM, int DOF>
+__host__ __device__ __forceinline__ void form_coefficients(int form, int slot, const double* prm, double shift, double t, const QPoint& q,
+                                                           int NA, int NV, double* C, double* fv) {
+  form_coefficients_rt<DIM>(form, slot, prm, shift, t, q, DOF, NA, NV, C, fv);
 }
 
 }  // namespace pc

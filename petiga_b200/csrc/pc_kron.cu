@@ -27,7 +27,8 @@ namespace pc {
 namespace {
 
 constexpr int kMaxTerms = 40;
-constexpr int kMaxWW = kMaxW * kMaxW;
+constexpr int kKronP = 4;               // the separable path keeps its pencil tables in static shared memory: degree <= 4
+constexpr int kMaxWW = (2 * kKronP + 1) * (2 * kKronP + 1);
 
 struct KronTerm { unsigned char ij, rs0, rs1, rs2; double c; };
 struct KronVTerm { unsigned char i, r0, r1, r2; double c; };
@@ -689,6 +690,7 @@ bool kron_applicable(const petiga_cuda_plan* P, int slot, int form) {
     if (slot == PETIGA_SLOT_SYSTEM && P->has_bc) return false;
   }
   if (L.dof > 3) return false;
+  for (int d = 0; d < L.dim; d++) if (L.ax[d].p > kKronP) return false;
   if (P->d_fixtable && L.nranks > 1) return false;          // table values of off-box columns are not local
   for (int d = 0; d < L.dim; d++)
     if (L.ax[d].periodic && L.ax[d].nnp < 2 * L.ax[d].p + 1) return false;

@@ -66,7 +66,7 @@ int build_layout(const petiga_cuda_space& sp, int rank, int nranks, Layout& L) {
     AxisLayout& a = L.ax[d];
     a.p = sp.p[d]; a.m = sp.m[d]; a.nel = sp.nel[d]; a.nnp = sp.nnp[d]; a.periodic = sp.periodic[d]; a.nqp = sp.nqp1[d];
     a.P = sp.proc_sizes[d]; a.r = sp.proc_ranks[d];
-    if (a.p < 0 || a.p > kMaxP) return fail(L, PETIGA_CUDA_ERR_SUP, "degree must be <= 4 on the device path");
+    if (a.p < 0 || a.p > kMaxP) return fail(L, PETIGA_CUDA_ERR_SUP, "degree must be <= 8 on the device path");
     if (d >= sp.dim && (a.p != 0 || a.nel != 1 || a.nnp != 1)) return fail(L, PETIGA_CUDA_ERR_ARG, "unused axes must be reset axes");
     if (!sp.U[d] || !sp.offset[d]) return fail(L, PETIGA_CUDA_ERR_ARG, "missing axis tables");
     const double* U = sp.U[d];

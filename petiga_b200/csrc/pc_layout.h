@@ -17,7 +17,7 @@
 
 namespace pc {
 
-constexpr int kMaxP = 4;              // device kernels are instantiated for p = 1..4
+constexpr int kMaxP = 8;              // tuned kernels are instantiated for p = 1..4, the generic kernel (pc_quadg.cuh) runs p <= 8
 constexpr int kMaxW = 2 * kMaxP + 1;  // widest 1-D stencil
 
 struct AxisLayout {

@@ -55,6 +55,7 @@ struct petiga_cuda_plan {
   double* d_rhs_loc = nullptr;     // [nloc*dof]
   double* d_U_loc = nullptr;       // [nloc*dof]
   double* d_V_loc = nullptr;
+  double* d_W_loc = nullptr;
   double* d_recv = nullptr; size_t recv_cap = 0;
   int* d_recv_rows = nullptr;      // concatenated recv row lists
   int64_t* d_recv_off = nullptr;   // same indexing: block offset of each listed row inside its peer's slab
@@ -67,7 +68,7 @@ struct petiga_cuda_plan {
   double* d_V_own = nullptr;
   double* d_scalar = nullptr; size_t scalar_cap = 0;   // [0,8): result, then per-CTA partials of compute_scalar
 
-  struct Slot { int form = -1; double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } slots[PETIGA_NSLOTS];
+  struct Slot { int form = -1; double prm[pc::kMaxPrm] = {0}; } slots[PETIGA_NSLOTS];
   int path = PETIGA_PATH_AUTO;
   int scatter = 0;
   std::vector<unsigned char> kron_cache;   // cached parameter block of the separable path
@@ -86,6 +87,8 @@ struct petiga_cuda_plan {
 
 namespace pc {
 void set_error(const std::string& msg);
+void nvtx_push(int slot);   // NVTX range named after the IGACompute* driver the slot stands for (no-op without libnvToolsExt)
+void nvtx_pop();
 int cuda_fail(cudaError_t e, const char* what);
 #define PC_CUDA(call)                                              \
   do {                                                             \
@@ -96,6 +99,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // quadrature path (pc_quad.cu)
 int launch_quadrature(petiga_cuda_plan* P, const KParams& base);      // v1: pair loop as one register-tiled contraction
 int launch_quadrature_sf(petiga_cuda_plan* P, const KParams& base);   // v2: sum-factorised
+int launch_quadrature_gen(petiga_cuda_plan* P, const KParams& base);  // generic runtime-degree kernel (pc_quadg.cu); also the face mode
 // separable path (pc_kron.cu)
 bool kron_applicable(const petiga_cuda_plan* P, int slot, int form);
 int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, double* rhs);
@@ -104,6 +108,5 @@ int exchange_ghost_rows(petiga_cuda_plan* P, int block, double* values, double* 
 int halo_state(petiga_cuda_plan* P, const double* U_own, double* U_loc);
 int nccl_load();
 // boundary-integral pass (pc_bnd.cu)
-bool form_has_boundary_term(int form);
 int launch_boundary_pass(petiga_cuda_plan* P, int slot, int form, const double* prm, double* rhs, bool apply_fix);
 }  // namespace pc

@@ -332,6 +332,7 @@ quad_kernel(const __grid_constant__ KParams prm) {
       int qi[3] = {q % nq1[0], (q / nq1[0]) % nq1[1], q / (nq1[0] * nq1[1])};
       double w = 1.0, J = 1.0;
       QPoint qp;
+      qp.atboundary = 0;
 #pragma unroll
       for (int d = 0; d < 3; d++) qp.x[d] = 0.0;
 #pragma unroll

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(SFCfg<DIM, P, DOF>::THREADS, MINB) quad_sf_ker
     for (int q = lt; q < nqp; q += G) {
       if (!(prm.per_qp || q == 0)) continue;
       QPoint qp;
+      qp.atboundary = 0;
 #pragma unroll
       for (int d = 0; d < 3; d++) qp.x[d] = Xq[d * nqp + q];
       if (state) {

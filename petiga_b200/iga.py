@@ -26,11 +26,18 @@ FORMS = {
     "CAHNHILLIARD2D": {"IFUNCTION": "IGADeviceForm_CahnHilliard2D_Residual", "IJACOBIAN": "IGADeviceForm_CahnHilliard2D_Tangent"},
     "CAHNHILLIARD3D": {"IFUNCTION": "IGADeviceForm_CahnHilliard3D_Residual", "IJACOBIAN": "IGADeviceForm_CahnHilliard3D_Tangent"},
     "BRATU": {"FUNCTION": "IGADeviceForm_Bratu_Function", "JACOBIAN": "IGADeviceForm_Bratu_Jacobian",
-              "IFUNCTION": "IGADeviceForm_Bratu_IFunction", "IJACOBIAN": "IGADeviceForm_Bratu_IJacobian"},
+              "IFUNCTION": "IGADeviceForm_Bratu_IFunction", "IJACOBIAN": "IGADeviceForm_Bratu_IJacobian",
+              "RHSFUNCTION": "IGADeviceForm_Bratu_RHSFunction", "RHSJACOBIAN": "IGADeviceForm_Bratu_RHSJacobian"},
+    "NITSCHE": {"SYSTEM": "IGADeviceForm_Nitsche_System"},
+    "SNES2D": {"FUNCTION": "IGADeviceForm_SNES2D_Function", "JACOBIAN": "IGADeviceForm_SNES2D_Jacobian"},
+    "PATTERNFORMATION": {"IEFUNCTION": "IGADeviceForm_PatternFormation_IEFunction", "IEJACOBIAN": "IGADeviceForm_PatternFormation_IEJacobian"},
+    "ELASTICROD": {"I2FUNCTION": "IGADeviceForm_ElasticRod_I2Function", "I2JACOBIAN": "IGADeviceForm_ElasticRod_I2Jacobian"},
 }
 _SETTERS = {"VECTOR": "IGASetFormVector", "MATRIX": "IGASetFormMatrix", "SYSTEM": "IGASetFormSystem",
             "FUNCTION": "IGASetFormFunction", "JACOBIAN": "IGASetFormJacobian", "IFUNCTION": "IGASetFormIFunction",
-            "IJACOBIAN": "IGASetFormIJacobian"}
+            "IJACOBIAN": "IGASetFormIJacobian", "IEFUNCTION": "IGASetFormIEFunction", "IEJACOBIAN": "IGASetFormIEJacobian",
+            "RHSFUNCTION": "IGASetFormRHSFunction", "RHSJACOBIAN": "IGASetFormRHSJacobian", "I2FUNCTION": "IGASetFormI2Function",
+            "I2JACOBIAN": "IGASetFormI2Jacobian"}
 
 
 class IGAComm(C.Structure):
@@ -277,6 +284,9 @@ class IGA:
         sym = FORMS[form][slot]
         fn = C.cast(getattr(self.H, sym), C.c_void_p)
         ctx = (C.c_double * max(1, len(params)))(*params)
+        if form == "PATTERNFORMATION" and len(params):      # the demo's AppCtx starts with a PetscBool (demo/PatternFormation.c:14-24)
+            C.cast(ctx, C.POINTER(C.c_int))[0] = int(params[0] != 0)
+            C.cast(ctx, C.POINTER(C.c_int))[1] = 0
         self._keep.append(ctx)
         _chk(getattr(self.H, _SETTERS[slot])(self.h, fn, C.cast(ctx, C.c_void_p) if len(params) else None))
 
@@ -313,6 +323,24 @@ class IGA:
 
     def ComputeIJacobian(self, a, V, t, U, J):
         _chk(self.H.IGAComputeIJacobian(self.h, C.c_double(a), V.h, C.c_double(t), U.h, J.h))
+
+    def ComputeIEFunction(self, a, V, t, U, t0, U0, F):
+        _chk(self.H.IGAComputeIEFunction(self.h, C.c_double(a), V.h, C.c_double(t), U.h, C.c_double(t0), U0.h, F.h))
+
+    def ComputeIEJacobian(self, a, V, t, U, t0, U0, J):
+        _chk(self.H.IGAComputeIEJacobian(self.h, C.c_double(a), V.h, C.c_double(t), U.h, C.c_double(t0), U0.h, J.h))
+
+    def ComputeRHSFunction(self, t, U, F):
+        _chk(self.H.IGAComputeRHSFunction(self.h, C.c_double(t), U.h, F.h))
+
+    def ComputeRHSJacobian(self, t, U, J):
+        _chk(self.H.IGAComputeRHSJacobian(self.h, C.c_double(t), U.h, J.h))
+
+    def ComputeI2Function(self, a, A, v, V, t, U, F):
+        _chk(self.H.IGAComputeI2Function(self.h, C.c_double(a), A.h, C.c_double(v), V.h, C.c_double(t), U.h, F.h))
+
+    def ComputeI2Jacobian(self, a, A, v, V, t, U, J):
+        _chk(self.H.IGAComputeI2Jacobian(self.h, C.c_double(a), A.h, C.c_double(v), V.h, C.c_double(t), U.h, J.h))
 
     def GetOwnedNaturalIndices(self):
         inf = self.info()

@@ -3,11 +3,12 @@ import numpy as np
 
 from tests.common import oracle_to_layout, rel_frobenius
 
-MAT_SLOTS = ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN")
-VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION")
+MAT_SLOTS = ("MATRIX", "SYSTEM", "JACOBIAN", "IJACOBIAN", "IEJACOBIAN", "RHSJACOBIAN", "I2JACOBIAN")
+VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION", "IEFUNCTION", "RHSFUNCTION", "I2FUNCTION")
 
 
-def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None, quad_impl=None):
+def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None, quad_impl=None,
+                W=None, shift2=0.0, t0=0.0):
     g = g or case.product()
     if quad_impl is not None:
         g.SetOption("quad_impl", quad_impl)
@@ -24,34 +25,43 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
         vU = g.CreateVec(); vU.set(U)
     if V is not None:
         vV = g.CreateVec(); vV.set(V)
-    if slot == "VECTOR": g.ComputeVector(B)
+    vW = None
+    if W is not None:
+        vW = g.CreateVec(); vW.set(W)
+    out_obj = A if slot in MAT_SLOTS else B
+    if slot in ("IEFUNCTION", "IEJACOBIAN"): g.ComputeIEFunction(shift, vV, t, vU, t0, vW, out_obj) if slot == "IEFUNCTION" else g.ComputeIEJacobian(shift, vV, t, vU, t0, vW, out_obj)
+    elif slot in ("RHSFUNCTION", "RHSJACOBIAN"): g.ComputeRHSFunction(t, vU, out_obj) if slot == "RHSFUNCTION" else g.ComputeRHSJacobian(t, vU, out_obj)
+    elif slot in ("I2FUNCTION", "I2JACOBIAN"): g.ComputeI2Function(shift, vW, shift2, vV, t, vU, out_obj) if slot == "I2FUNCTION" else g.ComputeI2Jacobian(shift, vW, shift2, vV, t, vU, out_obj)
+    elif slot == "VECTOR": g.ComputeVector(B)
     elif slot == "MATRIX": g.ComputeMatrix(A)
     elif slot == "SYSTEM": g.ComputeSystem(A, B)
     elif slot == "FUNCTION": g.ComputeFunction(vU, B)
     elif slot == "JACOBIAN": g.ComputeJacobian(vU, A)
     elif slot == "IFUNCTION": g.ComputeIFunction(shift, vV, t, vU, B)
     elif slot == "IJACOBIAN": g.ComputeIJacobian(shift, vV, t, vU, A)
-    out = dict(path=int(g.GetStat("last_path")), g=g)
+    out = dict(path=int(g.GetStat("last_path")), impl=int(g.GetStat("last_impl")), g=g)
     if A is not None:
         out["rowptr"], out["colidx"] = A.pattern()
         out["values"] = A.values()
         out["baij"] = A.baij
     if B is not None:
         out["rhs"] = B.get()
-    for v in (A, B, vU, vV, vT):
+    for v in (A, B, vU, vV, vT, vW):
         if v is not None:
             v.destroy()
     return out
 
 
-def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12, quad_impl=None):
+def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12, quad_impl=None,
+                         W=None, shift2=0.0, t0=0.0):
     """Pattern bit-exact; values / vectors within `tol` relative Frobenius error (north_star: 1e-12)."""
     o = case.oracle()
     if fixtable is not None:
         o.fixtable(fixtable)
     o.setup()
-    Ko, Fo = o.assemble(slot, form, params, shift=shift, V=V, t=t, U=U)
-    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable, quad_impl=quad_impl)
+    Ko, Fo = o.assemble(slot, form, params, shift=shift, V=V, t=t, U=U, W=W, shift2=shift2, t0=t0)
+    res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable, quad_impl=quad_impl,
+                      W=W, shift2=shift2, t0=t0)
     rp_o, ci_o, _ = o.pattern()
     errs = {}
     if Ko is not None:
