@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "quadrature"])
     ap.add_argument("--mesh", type=int, default=128)
     ap.add_argument("--geometry", default="identity", choices=["identity", "perturbed"])
-    ap.add_argument("--quad-impl", type=int, default=0, help="0 = sum-factorised quadrature kernel, 1 = pair-loop kernel")
+    ap.add_argument("--quad-impl", type=int, default=-1, help="-1 = library choice, 0 = sum-factorised (v2), 1 = pair-loop, 2 = generic, 3 = persistent DMMA kernel (v3)")
     ap.add_argument("--cpu-threads", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -702,8 +702,16 @@ int petiga_cuda_compute_ext(petiga_cuda_plan* P, int slot, int block, double shi
   int impl = P->quad_impl, rc;
   if (need_gen) { impl = 2; rc = launch_quadrature_gen(P, kp); }
   else {
-    if (impl < 0) impl = (L.dim == 3 && L.ax[0].p >= 2) ? 0 : 1;
-    rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+    rc = PETIGA_CUDA_ERR_SUP;
+    if (impl < 0 || impl == 3) {   // third-generation kernel where it applies (3-D, p = 3, dof 1, constant-coefficient linear forms)
+      rc = launch_quadrature_sf3(P, kp);
+      if (rc == 0) impl = 3;
+      else if (rc != PETIGA_CUDA_ERR_SUP || impl == 3) return rc;
+    }
+    if (rc == PETIGA_CUDA_ERR_SUP) {
+      if (impl < 0) impl = (L.dim == 3 && L.ax[0].p >= 2) ? 0 : 1;
+      rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);
+    }
     if (rc == PETIGA_CUDA_ERR_SUP && P->quad_impl < 0) {
       impl = 1 - impl;
       rc = impl == 1 ? launch_quadrature(P, kp) : launch_quadrature_sf(P, kp);

@@ -34,6 +34,7 @@ struct petiga_cuda_plan {
   double* d_kron1d[3] = {nullptr, nullptr, nullptr};
   double* d_kronrow[3] = {nullptr, nullptr, nullptr};   // 1-D global banded matrices [4][nnp][kMaxW]
   double* d_sfpp[3] = {nullptr, nullptr, nullptr};      // pair-product tables of the sum-factorised kernel
+  double* d_sf3pp[3] = {nullptr, nullptr, nullptr};     // the same products in the fragment layout of the third-generation kernel
 
   // pattern (owned by the plan), per block mode
   int* d_rowptr[2] = {nullptr, nullptr};
@@ -99,6 +100,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // quadrature path (pc_quad.cu)
 int launch_quadrature(petiga_cuda_plan* P, const KParams& base);      // v1: pair loop as one register-tiled contraction
 int launch_quadrature_sf(petiga_cuda_plan* P, const KParams& base);   // v2: sum-factorised
+int launch_quadrature_sf3(petiga_cuda_plan* P, const KParams& base);  // v3: persistent, warp-specialised, DMMA (3-D, p = 3, dof 1)
 int launch_quadrature_gen(petiga_cuda_plan* P, const KParams& base);  // generic runtime-degree kernel (pc_quadg.cu); also the face mode
 // separable path (pc_kron.cu)
 bool kron_applicable(const petiga_cuda_plan* P, int slot, int form);

@@ -10,8 +10,6 @@ namespace pc {
 
 // ------------------------------------------------------------------------------------------------------------
 // sum-factorised kernel (pc_quad2.cuh): component lists and launch
-namespace {
-
 template <int DIM, int DOF>
 void host_matrix_pattern(int form, int slot, const double* prm, const FormInfo& fi, std::vector<char>& pat, int& ijmask, std::vector<double>& Cout) {
   const int NA = fi.mc1 - fi.mc0;
@@ -142,6 +140,10 @@ int build_sf_lists(const KParams& kp, const FormInfo& fi, bool mapped, bool rati
   if (bad || nf > 16) return PETIGA_CUDA_ERR_SUP;
   return 0;
 }
+
+template void host_matrix_pattern<3, 1>(int, int, const double*, const FormInfo&, std::vector<char>&, int&, std::vector<double>&);
+
+namespace {
 
 template <int DIM, int P, int DOF, int NQ>
 int launch_sf_nq(petiga_cuda_plan* Pl, SFParams& sp) {

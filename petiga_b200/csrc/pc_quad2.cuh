@@ -47,8 +47,17 @@ struct SFParams {
   int const_dp;                   // 1: D'[pair][q] = JW_q * cconst[ij][pair]
 };
 
+}  // namespace pc
+#include <vector>
+namespace pc {
+// host side (pc_quad2.cu), shared with the third-generation kernel (pc_quad3.cu)
+template <int DIM, int DOF>
+void host_matrix_pattern(int form, int slot, const double* prm, const FormInfo& fi, std::vector<char>& pat, int& ijmask, std::vector<double>& Cout);
+int build_sf_lists(const KParams& kp, const FormInfo& fi, bool mapped, bool rational, bool state, bool transient,
+                   const std::vector<char>& cpat, int ijmask, SFLists& l);
+
 // plan-level table: PP[e][os*3+ot][q][a*n+b]
-__global__ void sf_pp_kernel(DevAxis ax, double* __restrict__ out) {
+static __global__ void sf_pp_kernel(DevAxis ax, double* __restrict__ out) {
   const int n = ax.nen, nq = ax.nqp, per = 9 * nq * n * n;
   const size_t total = (size_t)ax.nel * per;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {

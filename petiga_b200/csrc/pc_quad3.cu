@@ -1,0 +1,85 @@
+// pc_quad3.cu -- launcher of the third-generation quadrature kernel (pc_quad3.cuh).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "pc_plan.h"
+#include "pc_quad3.cuh"
+
+namespace pc {
+
+int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
+  const int dim = base.dim, dof = base.dof;
+  auto nope = [](const char* why) { set_error(std::string("quad_sf3: ") + why); return PETIGA_CUDA_ERR_SUP; };
+  if (dim != 3 || dof != 1) return nope("3-D, one dof per node only");
+  for (int d = 0; d < 3; d++) if (base.ax[d].p != 3 || base.ax[d].nqp != 4) return nope("degree 3 with the default 4-point rule only");
+  if (base.Wt) return nope("rational geometry runs the second-generation kernel");
+  if (base.slot != PETIGA_SLOT_VECTOR && base.slot != PETIGA_SLOT_MATRIX && base.slot != PETIGA_SLOT_SYSTEM) return nope("linear drivers only");
+  FormInfo fi = form_info(base.form, base.slot, dim, dof);
+  if (!fi.valid || !fi.mat_const || fi.order > 1 || fi.needs_state || base.U) return nope("constant-coefficient first-order forms only");
+  const bool mapped = base.X != nullptr;
+  SF3Params sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.k = base;
+  const int NA = base.mc1 - base.mc0, NV = base.vc1 - base.vc0;
+  if (NA > 4 || NV > 4) return nope("too many components");
+  // the form's constant coefficient tensor and vector (evaluated once on the host at a dummy point)
+  std::vector<double> C((size_t)std::max(NA * NA, 1), 0.0), fv((size_t)std::max(NV, 1), 0.0);
+  {
+    QPoint q;
+    memset(&q, 0, sizeof(q));
+    form_coefficients<3, 1>(base.form, base.slot, base.prm, base.shift, base.t, q, NA, NV, NA ? C.data() : nullptr, NV ? fv.data() : nullptr);
+  }
+  std::vector<char> cpat((size_t)std::max(NA * NA, 1), 0);
+  for (int k = 0; k < NA * NA; k++) { cpat[k] = C[k] != 0.0; sp.Cc[k] = C[k]; }
+  for (int k = 0; k < NV; k++) sp.fconst[k] = fv[k];
+  int rc = build_sf_lists(base, fi, mapped, false, false, false, cpat, NA > 0 ? 1 : 0, sp.l);
+  if (rc) return nope("component lists");
+  if (sp.l.NT > 4 || sp.l.npairs > k3MaxPairs || sp.l.ng2 > 4) return nope("too many tensor components");
+  for (int t = 0; t < sp.l.NT; t++) for (int d = 0; d < 3; d++) if (sp.l.torder[t][d] > 1) return nope("second derivatives");
+  // per-axis pair-product tables in the fragment layout, once per plan
+  for (int d = 0; d < 3; d++) {
+    if (!Pl->d_sf3pp[d]) {
+      const size_t n = (size_t)base.ax[d].nel * 576;
+      void* buf = nullptr;
+      PC_CUDA(cudaMalloc(&buf, n * sizeof(double)));
+      Pl->allocs.push_back(buf);
+      Pl->d_sf3pp[d] = (double*)buf;
+      sf3_pp_kernel<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, Pl->stream>>>(base.ax[d], Pl->d_sf3pp[d]);
+      PC_CUDA(cudaGetLastError());
+      Pl->launches++;
+    }
+    sp.pp[d] = Pl->d_sf3pp[d];
+  }
+  sp.const_dp = 0;
+  if (!mapped && NA > 0) {   // identity geometry: D'[pair] = JW * C[phys(s)][phys(t)]
+    sp.const_dp = 1;
+    auto phys_of = [&](int t) -> int {
+      if (t == sp.l.tN) return 0;
+      for (int d = 0; d < 3; d++) if (t == sp.l.tG[d]) return 1 + d;
+      return 4;
+    };
+    for (int pr = 0; pr < sp.l.npairs; pr++) {
+      const int al = phys_of(sp.l.pair_s[pr]) - base.mc0, be = phys_of(sp.l.pair_t[pr]) - base.mc0;
+      sp.cconst[pr] = (al >= 0 && al < NA && be >= 0 && be < NA) ? C[(size_t)al * NA + be] : 0.0;
+    }
+  }
+  sp.npencils = base.ax[1].ew * base.ax[2].ew;
+  sp.fixsys = (base.slot == PETIGA_SLOT_SYSTEM && base.any_bc) ? 1 : 0;
+  const SF3Smem lay;
+  const size_t smem = (size_t)lay.total * 8;
+  PC_CUDA(cudaFuncSetAttribute(quad_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = std::min(sp.npencils, Pl->num_sms);
+  if (blocks > 0 && base.nelem > 0) {
+    quad_sf3_kernel<<<blocks, k3Threads, smem, Pl->stream>>>(sp);
+    PC_CUDA(cudaGetLastError());
+    Pl->launches++;
+  }
+  // FP64 operations executed per element: DMMA count x 512, plus the FMA stages of the geometry group
+  const double dmmas = NA > 0 ? 8.0 * sp.l.npairs + 16.0 * sp.l.ng1 + 64.0 * sp.l.ng2 : 0.0;
+  const double geo = (mapped ? 2.0 * 4 * (384 + 576 + 768) + 200.0 * 64 : 0.0) + (NV > 0 ? 2.0 * 4 * sp.l.NT * (64 + 64 + 64) : 0.0) + (NA > 0 ? 2.0 * sp.l.npairs * 64 : 0.0);
+  Pl->last_flops = (double)base.nelem * (dmmas * 512.0 + geo);
+  return 0;
+}
+
+}  // namespace pc

@@ -1,0 +1,70 @@
+"""GPU parity of the third-generation quadrature kernel (pc_quad3.cuh: persistent pencils, DMMA stages, shared-memory window,
+cp.async.bulk + mbarrier ring) against the CPU oracle: everything it accepts, forced with quad_impl = 3."""
+import numpy as np
+import pytest
+
+from tests.common import Case
+from tests.gpu_common import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def dall(v=1.0):
+    return [(d, s, 0, v) for d in range(3) for s in range(2)]
+
+
+@pytest.mark.parametrize("N", [4, (5, 3, 6), (9, 2, 3), (1, 1, 1), (2, 7, 1)])
+def test_sf3_poisson_identity(N):
+    res, _ = check_against_oracle(Case(3, p=3, N=N, bcv=dall()), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL)
+    assert res["impl"] == 3
+
+
+@pytest.mark.parametrize("N", [4, (6, 3, 5)])
+def test_sf3_poisson_mapped(N):
+    res, _ = check_against_oracle(Case(3, p=3, N=N, bcv=dall(0.5), geometry=("perturbed", 0.05)), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL)
+    assert res["impl"] == 3
+
+
+@pytest.mark.parametrize("C", [0, 1, 2])
+def test_sf3_lower_continuity_and_periodic(C):
+    """C < p-1: the window advances by p - C rows per element; periodic axes wrap the row slots."""
+    check_against_oracle(Case(3, p=3, N=(4, 3, 3), C=C, bcv=dall()), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL)
+    check_against_oracle(Case(3, p=3, N=(8, 7, 9), C=C, periodic=(True, False, True)), "SYSTEM", "MASS", path="quadrature", quad_impl=3, tol=TOL)
+
+
+def test_sf3_other_forms_and_slots():
+    case = Case(3, p=3, N=(4, 5, 3), limits=(-1.0, 1.0))
+    for choice in (0, 4, 6):
+        check_against_oracle(case, "SYSTEM", "L2PROJECTION", [choice], path="quadrature", quad_impl=3, tol=TOL)
+    for slot in ("SYSTEM", "MATRIX", "VECTOR"):
+        check_against_oracle(case, slot, "MASS", path="quadrature", quad_impl=3, tol=TOL)
+    bcv = [(d, 0, 0, 1.0) for d in range(3)]
+    bcl = [(d, 1, 0, 0.25 * (d + 1)) for d in range(3)]
+    check_against_oracle(Case(3, p=3, N=4, bcv=bcv, bcl=bcl), "SYSTEM", "LAPLACE", path="quadrature", quad_impl=3, tol=TOL)
+    check_against_oracle(Case(3, p=3, N=4, bcv=bcv, bcl=bcl, geometry=("perturbed", 0.05)), "SYSTEM", "LAPLACE", path="quadrature", quad_impl=3, tol=TOL)
+    bcl = [(d, s, 0, (2 * s - 1) * 6.283185307179586) for d in range(3) for s in range(2)]
+    check_against_oracle(Case(3, p=3, N=4, bcl=bcl), "SYSTEM", "NEUMANN", path="quadrature", quad_impl=3, tol=TOL)
+    check_against_oracle(Case(3, p=3, N=4, bcv=dall(0.0)), "SYSTEM", "CONVTEST", [1.5, 0.75], path="quadrature", quad_impl=3, tol=TOL)
+    check_against_oracle(Case(3, p=3, N=4, bcv=dall(0.0), geometry=("perturbed", 0.05)), "SYSTEM", "CONVTEST", [1.5, 0.75], path="quadrature", quad_impl=3, tol=TOL)
+
+
+def test_sf3_fixtable():
+    case = Case(3, p=3, N=4, bcv=dall())
+    table = np.random.default_rng(21).standard_normal(7 ** 3)
+    check_against_oracle(case, "SYSTEM", "POISSON", fixtable=table, path="quadrature", quad_impl=3, tol=TOL)
+
+
+def test_sf3_midsize_many_pencils_per_cta():
+    """More pencils than SMs: every CTA walks several pencils (ring parity, window reuse across pencils)."""
+    from tests.gpu_common import run_product
+    from tests.common import rel_frobenius
+    case = Case(3, p=3, N=(20, 16, 14), bcv=[(d, s, 0, 1.0 + d - 0.5 * s) for d in range(3) for s in range(2)])
+    a = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=3)
+    b = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=0)
+    assert a["impl"] == 3 and b["impl"] == 0
+    assert rel_frobenius(a["values"], b["values"]) <= TOL and rel_frobenius(a["rhs"], b["rhs"]) <= TOL
+    case = Case(3, p=3, N=(20, 16, 14), bcv=dall(), geometry=("perturbed", 0.05))
+    a = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=3)
+    b = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=0)
+    assert rel_frobenius(a["values"], b["values"]) <= TOL and rel_frobenius(a["rhs"], b["rhs"]) <= TOL
