@@ -340,7 +340,7 @@ int petiga_cuda_plan_destroy(petiga_cuda_plan* P) {
   for (void* d : P->allocs) cudaFree(d);
   for (int b = 0; b < 2; b++) { cudaFree(P->d_rowptr[b]); cudaFree(P->d_colidx[b]); }
   cudaFree(P->d_X); cudaFree(P->d_W); cudaFree(P->d_fixtable); cudaFree(P->d_ghost_values); cudaFree(P->d_recv);
-  cudaFree(P->d_scalar); cudaFree(P->d_values_own); cudaFree(P->d_rhs_own); cudaFree(P->d_U_own); cudaFree(P->d_V_own);
+  cudaFree(P->d_scalar); cudaFree(P->d_sf3_dprime); cudaFree(P->d_values_own); cudaFree(P->d_rhs_own); cudaFree(P->d_U_own); cudaFree(P->d_V_own);
   if (P->h_pinned) cudaFreeHost(P->h_pinned);
   if (P->ev0) cudaEventDestroy(P->ev0);
   if (P->ev1) cudaEventDestroy(P->ev1);

@@ -66,11 +66,37 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
   }
   sp.npencils = base.ax[1].ew * base.ax[2].ew;
   sp.fixsys = (base.slot == PETIGA_SLOT_SYSTEM && base.any_bc) ? 1 : 0;
-  const SF3Smem lay;
-  const size_t smem = (size_t)lay.total * 8;
-  PC_CUDA(cudaFuncSetAttribute(quad_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int blocks = std::min(sp.npencils, Pl->num_sms);
-  if (blocks > 0 && base.nelem > 0) {
+  sp.want_mat = (NA > 0 && slot_has_mat(base.slot)) ? 1 : 0;
+  sp.want_vec = slot_has_vec(base.slot) ? 1 : 0;
+  {  // pencil segments: the axis-0 rows of a segment must fit the shared-memory tables
+    const AxisLayout& a0 = Pl->L.ax[0];
+    // rows advance by (offset[e+1] - offset[e]) per element: 1 on a maximally smooth axis, at most p + 1 otherwise
+    const int maxstep = (a0.nnp == a0.nel + a0.p || (a0.periodic && a0.nnp == a0.nel)) ? 1 : a0.p + 1;
+    sp.seglen = std::max(1, std::min(k3MaxSeg, (k3MaxRows - 4) / maxstep + 1));
+    sp.nseg = (a0.ew + sp.seglen - 1) / sp.seglen;
+  }
+  if (base.nelem <= 0) return 0;
+  if (mapped && sp.want_mat) {   // D' scratch of the geometry pre-pass: [local element][pair][64]
+    const size_t need = (size_t)base.nelem * sp.l.npairs * 64;
+    if (Pl->sf3_dprime_cap < need) {
+      cudaFree(Pl->d_sf3_dprime);
+      Pl->d_sf3_dprime = nullptr; Pl->sf3_dprime_cap = 0;
+      PC_CUDA(cudaMalloc(&Pl->d_sf3_dprime, need * sizeof(double)));
+      Pl->sf3_dprime_cap = need;
+    }
+    sp.dprime = Pl->d_sf3_dprime;
+  }
+  if ((mapped && sp.want_mat) || sp.want_vec) {
+    sf3_geom_kernel<<<base.nelem, 64, 0, Pl->stream>>>(sp);
+    PC_CUDA(cudaGetLastError());
+    Pl->launches++;
+  }
+  if (sp.want_mat) {
+    const SF3Smem lay(sp.l.npairs, mapped ? 1 : 0);
+    const size_t smem = (size_t)lay.total * 8;
+    if (smem > 227 * 1024) return nope("shared memory");
+    PC_CUDA(cudaFuncSetAttribute(quad_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = std::min(sp.npencils * sp.nseg, Pl->num_sms);
     quad_sf3_kernel<<<blocks, k3Threads, smem, Pl->stream>>>(sp);
     PC_CUDA(cudaGetLastError());
     Pl->launches++;
