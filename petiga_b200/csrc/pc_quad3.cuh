@@ -71,13 +71,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   while (!ok)
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(s3_u32(b)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) {   // the producer's wait: do not burn issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) {   // the producer's wait: suspend instead of polling
   uint32_t ok = 0;
-  for (;;) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(s3_u32(b)), "r"(parity) : "memory");
-    if (ok) break;
-    __nanosleep(200);
-  }
+  while (!ok)   // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the time is up
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(s3_u32(b)), "r"(parity), "r"(20000u) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -461,7 +459,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
     }
     bar_asm();
     // flush tables of this lane for the whole work item: entry k of row rr of this warp -> window offset, position coefficients
-    int fso[2][4], fP1[2][4], fP23[2][4];
+    int fso[2][4], fP1[2][4], fP23[2][4], fP13[2][4];
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
       const int a12 = 2 * warp + rr, a1 = a12 & 3, a2 = a12 >> 2;
@@ -472,6 +470,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
         fso[rr][k] = (a2 * 7 + c0) * k3SRow + a1 * 20 + (bb & 3) * 4 + (bb >> 2);
         fP1[rr][k] = (int)(ptv & 0xFFFF);
         fP23[rr][k] = (int)(ptv >> 16);
+        fP13[rr][k] = (int)(ptv & 0xFFFF) + (int)(ptv >> 24);          // storage-order rows: pos = (P1 + P3) W0 + c0 - c0first
       }
     }
     for (int le = 0; le < nel; le++, it++) {
@@ -598,13 +597,13 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
           const int64_t ro = rowoffT[row * 16 + 2 * warp + rr];
           double* dst = ((ro >> 62) & 1) ? prm.ghost_values + (ro & (((int64_t)1 << 62) - 1)) : prm.values + ro;
           if (row_simple) {
+            double* dstc = dst - c0first;
+            double vv[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              if (k == 3 && lane >= 16) break;
-              double* sp0 = srow + fso[rr][k];
-              const double v = *sp0;
-              if (v != 0.0) { atomicAdd(dst + (fP1[rr][k] + (fP23[rr][k] >> 8)) * W0 + fc0[k] - c0first, v); *sp0 = 0.0; }
-            }
+            for (int k = 0; k < 4; k++) vv[k] = (k == 3 && lane >= 16) ? 0.0 : srow[fso[rr][k]];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (vv[k] != 0.0) { atomicAdd(dstc + (fP13[rr][k] * W0 + fc0[k]), vv[k]); srow[fso[rr][k]] = 0.0; }
           } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
