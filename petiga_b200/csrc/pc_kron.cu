@@ -74,7 +74,10 @@ __global__ void kron_1d_kernel(DevAxis ax, const int* __restrict__ first, double
     const int r = rs >> 1, s = rs & 1;
     const int col = wrapi(first[i] + c, nnp);
     double acc = 0.0;
-    for (int e = 0; e < ax.nel; e++) {
+    // a 1-D row has at most 2p+1 columns; beyond them (the table rows are kMaxW wide) and, without periodicity, beyond the last
+    // node the entry is zero -- a wrapped index must not fold back into the row's support on short axes
+    const bool exists = c <= 2 * ax.p && (ax.periodic || first[i] + c < nnp);
+    for (int e = 0; e < (exists ? ax.nel : 0); e++) {
       int a = -1, b = -1;
       for (int l = 0; l < nen; l++) {
         int node = wrapi(ax.offset[e] + l, nnp);

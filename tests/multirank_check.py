@@ -53,6 +53,18 @@ def main():
         ("cahnhilliard IF", Case(2, p=2, N=32, C=1, periodic=True), "IFUNCTION", "CAHNHILLIARD2D", [1.5, 3000.0], True),
         ("bratu F", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "FUNCTION", "BRATU", [6.8], True),
         ("bratu J", Case(3, p=2, N=8, bcv=dall(3, 0.0)), "JACOBIAN", "BRATU", [6.8], True),
+        # round 2: third-generation kernel on mapped geometry, generic kernel (mixed degrees, order-2 on mapped geometry),
+        # boundary-integral matrix terms, IE / I2 / RHS drivers
+        ("mapped poisson p3", Case(3, p=3, N=(8, 6, 8), geometry=("perturbed", 0.05), bcv=dall(3)), "SYSTEM", "POISSON", [], False),
+        ("mixed degree mass", Case(2, dof=3, p=(2, 3), N=(10, 12), periodic=(False, True)), "SYSTEM", "MASS", [], False),
+        ("dof 5 mass", Case(2, dof=5, p=(4, 3), N=(8, 9)), "SYSTEM", "MASS", [], False),
+        ("nitsche 2d", Case(2, p=2, N=(12, 10), bcf=[(d, s) for d in range(2) for s in range(2)]), "SYSTEM", "NITSCHE", [], False),
+        ("nitsche 3d mapped", Case(3, p=2, N=6, geometry=("perturbed", 0.05), bcf=[(d, s) for d in range(3) for s in range(2)]), "SYSTEM", "NITSCHE", [], False),
+        ("ch2d mapped IJ", Case(2, p=2, N=(12, 10), order=2, geometry=("perturbed", 0.05)), "IJACOBIAN", "CAHNHILLIARD2D", [1.5, 3000.0], True),
+        ("patternform IEJ", Case(2, dof=2, p=2, N=(16, 12), limits=(-1.0, 1.0), periodic=True), "IEJACOBIAN", "PATTERNFORMATION", [1.0, 0.0045, 0.5, 1.0, 0.899, -0.910, -0.899, 0.020, 0.200], True),
+        ("patternform IEF", Case(2, dof=2, p=2, N=(16, 12), limits=(-1.0, 1.0), periodic=True), "IEFUNCTION", "PATTERNFORMATION", [0.0, 0.0045, 0.5, 1.0, 0.899, -0.910, -0.899, 0.020, 0.200], True),
+        ("elasticrod I2F", Case(1, p=2, N=32, bcv=[(0, 0, 0, 0.0), (0, 1, 0, 0.0)]), "I2FUNCTION", "ELASTICROD", [1.3, 0.7], True),
+        ("bratu RHSJ", Case(2, p=2, N=(12, 10), bcv=dall(2, 0.0)), "RHSJACOBIAN", "BRATU", [2.0], True),
     ]
     nfail = 0
     for name, case, slot, form, prm, state in cases:
@@ -60,22 +72,30 @@ def main():
         o.setup()
         rp, ci, rs = o.pattern(world)
         n = len(rp) - 1
-        U = V = None
+        U = V = W = None
         if state:
             U, V = state_vectors(n * case.dof)
-        Ko, Fo = o.assemble(slot, form, prm, size=world, shift=7.0, V=V, U=U)
+            if slot.startswith("IE") or slot.startswith("I2"):
+                W = np.random.default_rng(5).random(n * case.dof)
+        Ko, Fo = o.assemble(slot, form, prm, size=world, shift=7.0, V=V, U=U, W=W, shift2=0.5, t0=0.1)
         r0, r1 = int(rs[rank]), int(rs[rank + 1])
         for path in (["quadrature", "auto"] if not state else ["quadrature"]):
             g = case.product(rank=rank, size=world, nccl=comm.value, device=local)
             Ul = None if U is None else U[r0 * case.dof:r1 * case.dof]
             Vl = None if V is None else V[r0 * case.dof:r1 * case.dof]
-            res = run_product(case, slot, form, prm, U=Ul, V=Vl if slot in ("IFUNCTION", "IJACOBIAN") else None, shift=7.0, path=path, g=g)
+            Wl = None if W is None else W[r0 * case.dof:r1 * case.dof]
+            needs_v = slot in ("IFUNCTION", "IJACOBIAN") or W is not None
+            res = run_product(case, slot, form, prm, U=Ul, V=Vl if needs_v else None, W=Wl, shift=7.0, shift2=0.5, t0=0.1, path=path, g=g)
             ok, msg = True, ""
             if slot in MAT_SLOTS:
                 rpl = rp[r0:r1 + 1] - rp[r0]
                 cil = ci[rp[r0]:rp[r1]]
                 if res["baij"] or case.dof == 1:
-                    ok &= bool(np.array_equal(res["rowptr"], rpl) and np.array_equal(res["colidx"], cil))
+                    pat_ok = bool(np.array_equal(res["rowptr"], rpl) and np.array_equal(res["colidx"], cil))
+                    if not pat_ok:
+                        msg += " PATTERN(rank %d: rowptr %s, colidx mismatches %d of %d)" % (
+                            rank, np.array_equal(res["rowptr"], rpl), int(np.sum(res["colidx"] != cil)) if len(res["colidx"]) == len(cil) else -1, len(cil))
+                    ok &= pat_ok
                 exp = oracle_to_layout(Ko[rp[r0]:rp[r1]], rpl, case.dof, res["baij"])
                 e = rel_frobenius(res["values"], exp)
                 ok &= e <= 1e-12
@@ -86,6 +106,8 @@ def main():
                 msg += " F=%.1e" % e
             flag = torch.tensor([0 if ok else 1], device="cuda")
             dist.all_reduce(flag)
+            if not ok and rank != 0:
+                print("rank %d: %-20s %-10s FAIL%s" % (rank, name, path, msg), flush=True)
             if rank == 0:
                 print("%-20s %-10s path=%d %s%s" % (name, path, res["path"], "ok " if flag.item() == 0 else "FAIL", msg), flush=True)
             nfail += int(flag.item() != 0)
