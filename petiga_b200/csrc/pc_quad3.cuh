@@ -26,8 +26,9 @@ constexpr int k3AsmThreads = 256, k3Threads = k3AsmThreads + 32;   // 8 assembly
 constexpr int k3Ring = 4;         // ring slots of (PP0 slice, D' block) filled by cp.async.bulk
 constexpr int k3U2Q = 388;        // q2 stride of U2 (16 rows of 24 + 4: conflict-free B fragments in stage C)
 constexpr int k3MaxPairs = 16;
-constexpr int k3SRow = 80;        // S inner block [a1 (stride 20)][b1 (4)][b2]
-constexpr int k3SSize = 4 * 4 * 7 * k3SRow;
+constexpr int k3SA = 113;         // window S[row slot (4)][a2][a1][e = c0 + 7 (b1 + 4 b2)]: 112 entries in flush (storage) order + 1 pad, so that
+constexpr int k3SSlot = 16 * k3SA; //   both the fragment update of stage C and the linear flush walk 16 distinct bank pairs per half-warp
+constexpr int k3SSize = 4 * k3SSlot;
 constexpr int k3MaxRows = 160;    // axis-0 rows of one pencil segment (tables live in shared memory)
 constexpr int k3MaxSeg = 157;     // elements of one pencil segment
 
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
       for (int k = 0; k < 4; k++) {
         const int c0 = fc0[k], bb = fbb[k] & 15;
         const uint32_t ptv = PT[a12 * 16 + bb];
-        fso[rr][k] = (a2 * 7 + c0) * k3SRow + a1 * 20 + (bb & 3) * 4 + (bb >> 2);
+        fso[rr][k] = (a2 * 4 + a1) * k3SA + lane + 32 * k;
         fP1[rr][k] = (int)(ptv & 0xFFFF);
         fP23[rr][k] = (int)(ptv >> 16);
         fP13[rr][k] = (int)(ptv & 0xFFFF) + (int)(ptv >> 24);          // storage-order rows: pos = (P1 + P3) W0 + c0 - c0first
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
         }
         // ---- Dirichlet fix-up on the fragments (petigaelem.c:1360-1389), then the shared-memory window ----
         const int a0 = warp >> 1;
-        double* sbase = S + ((i0 + a0) & 3) * (4 * 7 * k3SRow) + (r >> 2) * (7 * k3SRow) + (c >> 1) * 20 + 8 * (c & 1) + (r & 3);
+        double* sbase = S + ((i0 + a0) & 3) * k3SSlot + ((r >> 2) * 4 + (c >> 1)) * k3SA + (2 * (c & 1) + 4 * (r & 3)) * 7;
         if (!elem_fix) {
 #pragma unroll
           for (int h = 0; h < 2; h++) {
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
               for (int mt = 0; mt < 2; mt++) {
-                double* sp0 = sbase + (2 * mt * 7 + c0) * k3SRow + 2 * nt * 20;
+                double* sp0 = sbase + (8 * mt + 2 * nt) * k3SA + c0;
                 sp0[0] += cC[h][nt][mt][0];
-                sp0[4] += cC[h][nt][mt][1];
+                sp0[7] += cC[h][nt][mt][1];
               }
           }
         } else {
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
 #pragma unroll
               for (int mt = 0; mt < 2; mt++) {
                 const int a2 = 2 * mt + (r >> 2), b2 = r & 3, a1 = 2 * nt + (c >> 1);
-                double* sp0 = sbase + (2 * mt * 7 + c0) * k3SRow + 2 * nt * 20;
+                double* sp0 = sbase + (8 * mt + 2 * nt) * k3SA + c0;
 #pragma unroll
                 for (int x = 0; x < 2; x++) {
                   double v = cC[h][nt][mt][x];
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
                     if (fcx && !fr) atomicAdd(&prm.rhs[rowlr[ra]], -v * fixval[cb]);
                     v = (ra == cb) ? 1.0 : 0.0;
                   }
-                  sp0[4 * x] += v;
+                  sp0[7 * x] += v;
                 }
               }
           }
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
       // ---- flush the row slots no later element of the segment touches: coalesced red.global.add.f64 ----
       for (int f = 0; f < nflush; f++) {
         const int row = i0 + f, W0 = W0T[row];
-        double* srow = S + (row & 3) * (4 * 7 * k3SRow);
+        double* srow = S + (row & 3) * k3SSlot;
         const uint32_t sfirst = seg0T[row * 8 + 3];                     // the diagonal column always exists
         // axis 0 in storage order: every existing column c0 has (Bi, Si, Li) = (0, W0, c0 - c0first), so
         // pos = P1 W0 + P2 Bi + P3 Si + Li = (P1 + P3) W0 + c0 - c0first whatever the owners along axes 1 and 2

@@ -74,6 +74,25 @@ __global__ void __launch_bounds__(256) red_kernel(double* buf, size_t n, int ite
   }
 }
 
+// same question with cheap addressing (the u64 modulo above costs more issue slots than the reduction itself): a warp adds to
+// `width` contiguous doubles (lanes >= width idle) at pseudo-random 256B-aligned places of a power-of-two buffer; mode 0 = red,
+// 1 = plain store, 2 = red of 4 consecutive 256B lines per address computation (a row's 112-entry flush)
+__global__ void __launch_bounds__(256) red2_kernel(double* buf, uint32_t mask32, int iters, int width, int mode) {
+  const int lane = threadIdx.x & 31;
+  uint32_t s = (blockIdx.x * 8u + (threadIdx.x >> 5)) * 0x9E3779B9u + 12345u;
+  const bool on = lane < width;
+  for (int i = 0; i < iters; i++) {
+    s = s * 1664525u + 1013904223u;
+    const uint32_t place = ((s >> 7) ^ (s << 9)) & mask32;
+    double* p = buf + (size_t)place * 32 + lane;
+    if (mode == 2) {
+      if (on) { atomicAdd(p, 1.0); atomicAdd(p + 32, 1.0); atomicAdd(p + 64, 1.0); atomicAdd(p + 96, 1.0); }
+    } else if (on) {
+      if (mode == 1) *p = 1.0; else atomicAdd(p, 1.0);
+    }
+  }
+}
+
 // shared-memory accumulation step of the planned kernel: S[idx] += v, conflict-free, vs ATOMS
 __global__ void __launch_bounds__(256) smem_acc_kernel(double* out, int iters) {
   __shared__ double S[5888];
@@ -189,6 +208,21 @@ int main() {
       }
       printf(", \"red_l2_pattern%d_Gops\": %.2f", pat, (double)blocks * 256 * iters / (best * 1e-3) / 1e9);
     }
+    // cheap-address versions: 4 GiB target (mask over 2^24 256-byte lines) and an L2-resident 64 MiB target
+    for (int l2 = 0; l2 < 2; l2++)
+      for (int cfg = 0; cfg < 5; cfg++) {
+        const int width = (cfg == 3) ? 28 : 32, mode = (cfg == 1) ? 1 : (cfg == 2 ? 2 : 0);
+        const int bl = (cfg == 4) ? sms : blocks;                   // cfg 4: one CTA of 8 warps per SM (the occupancy of quad_sf3)
+        const uint32_t mask = l2 ? ((1u << 18) - 1) : ((1u << 24) - 1);
+        float best = 1e30f;
+        for (int it = 0; it < 3; it++) {
+          CK(cudaEventRecord(e0)); red2_kernel<<<bl, 256>>>(buf, mask, iters, width, mode); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+          best = fminf(best, time_ms(e0, e1));
+        }
+        const double ops = (double)bl * 8 * width * iters * (mode == 2 ? 4 : 1);
+        static const char* nm[5] = {"red32", "store32", "red4x32", "red28", "red32_1cta"};
+        printf(", \"%s_%s_Gops\": %.2f", nm[cfg], l2 ? "l2" : "dram", ops / (best * 1e-3) / 1e9);
+      }
     CK(cudaFree(buf));
   }
   // ---- smem accumulate ----
