@@ -4,7 +4,7 @@
 #include <vector>
 
 #include "pc_plan.h"
-#include "pc_quad3.cuh"
+#include "pc_quad3r.cuh"
 
 namespace pc {
 
@@ -68,10 +68,12 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
   sp.fixsys = (base.slot == PETIGA_SLOT_SYSTEM && base.any_bc) ? 1 : 0;
   sp.want_mat = (NA > 0 && slot_has_mat(base.slot)) ? 1 : 0;
   sp.want_vec = slot_has_vec(base.slot) ? 1 : 0;
+  bool smooth0 = false;
   {  // pencil segments: the axis-0 rows of a segment must fit the shared-memory tables
     const AxisLayout& a0 = Pl->L.ax[0];
     // rows advance by (offset[e+1] - offset[e]) per element: 1 on a maximally smooth axis, at most p + 1 otherwise
     const int maxstep = (a0.nnp == a0.nel + a0.p || (a0.periodic && a0.nnp == a0.nel)) ? 1 : a0.p + 1;
+    smooth0 = (maxstep == 1);
     sp.seglen = std::max(1, std::min(k3MaxSeg, (k3MaxRows - 4) / maxstep + 1));
     sp.nseg = (a0.ew + sp.seglen - 1) / sp.seglen;
   }
@@ -92,12 +94,21 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
     Pl->launches++;
   }
   if (sp.want_mat) {
-    const SF3Smem lay(sp.l.npairs, mapped ? 1 : 0);
-    const size_t smem = (size_t)lay.total * 8;
-    if (smem > 227 * 1024) return nope("shared memory");
-    PC_CUDA(cudaFuncSetAttribute(quad_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = std::min(sp.npencils * sp.nseg, Pl->num_sms);
-    quad_sf3_kernel<<<blocks, k3Threads, smem, Pl->stream>>>(sp);
+    const SF3RSmem layr(sp.l.npairs, mapped ? 1 : 0);
+    if (smooth0 && Pl->sf3_variant == 0 && (size_t)layr.total * 8 <= 227 * 1024) {   // rows carried in the DMMA accumulators
+      const size_t smem = (size_t)layr.total * 8;
+      PC_CUDA(cudaFuncSetAttribute(quad_sf3r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      quad_sf3r_kernel<<<blocks, k3rThreads, smem, Pl->stream>>>(sp);
+      Pl->last_sf3_variant = 0;
+    } else {
+      const SF3Smem lay(sp.l.npairs, mapped ? 1 : 0);
+      const size_t smem = (size_t)lay.total * 8;
+      if (smem > 227 * 1024) return nope("shared memory");
+      PC_CUDA(cudaFuncSetAttribute(quad_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      quad_sf3_kernel<<<blocks, k3Threads, smem, Pl->stream>>>(sp);
+      Pl->last_sf3_variant = 1;
+    }
     PC_CUDA(cudaGetLastError());
     Pl->launches++;
   }

@@ -67,10 +67,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrie
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag = 0) {
   uint32_t ok = 0;
-  while (!ok)
+#ifdef PC_SF3_DEBUG
+  long long spins = 0;
+#endif
+  while (!ok) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(s3_u32(b)), "r"(parity) : "memory");
+#ifdef PC_SF3_DEBUG
+    if (++spins > 2000000) { if ((threadIdx.x & 31) == 0) printf("mbar_wait hang: block %d tid %d tag %d parity %u\n", blockIdx.x, threadIdx.x, tag, parity); __trap(); }
+#endif
+  }
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) {   // the producer's wait: suspend instead of polling
   uint32_t ok = 0;
@@ -505,10 +512,11 @@ __global__ void __launch_bounds__(k3Threads, 1) quad_sf3_kernel(const __grid_con
           }
           const double* pb = PP1 + ls.g1_oo1[g1] * 64 + lane;
           const double b0 = pb[0], b1 = pb[32];
-          dmma(cB[0][0][0], cB[0][0][1], cA[0][x], b0);
-          dmma(cB[0][1][0], cB[0][1][1], cA[0][x], b1);
-          dmma(cB[1][0][0], cB[1][0][1], cA[1][x], b0);
-          dmma(cB[1][1][0], cB[1][1][1], cA[1][x], b1);
+          const double ax0 = x ? cA[0][1] : cA[0][0], ax1 = x ? cA[1][1] : cA[1][0];   // (a select, not a dynamic index: no local memory)
+          dmma(cB[0][0][0], cB[0][0][1], ax0, b0);
+          dmma(cB[0][1][0], cB[0][1][1], ax0, b1);
+          dmma(cB[1][0][0], cB[1][0][1], ax1, b0);
+          dmma(cB[1][1][0], cB[1][1][1], ax1, b1);
         }
         double* u = U2 + (g2 * 4 + q2) * k3U2Q + r * 24 + 2 * c;     // U2[g2][q2][ab0 * 24 + ab1]
 #pragma unroll

@@ -8,8 +8,10 @@ VEC_SLOTS = ("VECTOR", "SYSTEM", "FUNCTION", "IFUNCTION", "IEFUNCTION", "RHSFUNC
 
 
 def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, g=None, quad_impl=None,
-                W=None, shift2=0.0, t0=0.0):
+                W=None, shift2=0.0, t0=0.0, options=None):
     g = g or case.product()
+    for name, value in (options or {}).items():
+        g.SetOption(name, value)
     if quad_impl is not None:
         g.SetOption("quad_impl", quad_impl)
     if path is not None:
@@ -39,7 +41,7 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
     elif slot == "JACOBIAN": g.ComputeJacobian(vU, A)
     elif slot == "IFUNCTION": g.ComputeIFunction(shift, vV, t, vU, B)
     elif slot == "IJACOBIAN": g.ComputeIJacobian(shift, vV, t, vU, A)
-    out = dict(path=int(g.GetStat("last_path")), impl=int(g.GetStat("last_impl")), g=g)
+    out = dict(path=int(g.GetStat("last_path")), impl=int(g.GetStat("last_impl")), sf3_variant=int(g.GetStat("last_sf3_variant")), g=g)
     if A is not None:
         out["rowptr"], out["colidx"] = A.pattern()
         out["values"] = A.values()
@@ -53,7 +55,7 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
 
 
 def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, path=None, fixtable=None, tol=1e-12, quad_impl=None,
-                         W=None, shift2=0.0, t0=0.0):
+                         W=None, shift2=0.0, t0=0.0, options=None):
     """Pattern bit-exact; values / vectors within `tol` relative Frobenius error (north_star: 1e-12)."""
     o = case.oracle()
     if fixtable is not None:
@@ -61,7 +63,7 @@ def check_against_oracle(case, slot, form, params=(), U=None, V=None, shift=0.0,
     o.setup()
     Ko, Fo = o.assemble(slot, form, params, shift=shift, V=V, t=t, U=U, W=W, shift2=shift2, t0=t0)
     res = run_product(case, slot, form, params, U=U, V=V, shift=shift, t=t, path=path, fixtable=fixtable, quad_impl=quad_impl,
-                      W=W, shift2=shift2, t0=t0)
+                      W=W, shift2=shift2, t0=t0, options=options)
     rp_o, ci_o, _ = o.pattern()
     errs = {}
     if Ko is not None:
