@@ -467,13 +467,14 @@ def sweep_configs(stream, peaks):
         nnz = (A.nnz * (case.dof ** 2 if A.baij else 1)) if A is not None else 0
         nvec = B.size if B is not None else 0
         path = {1: "quadrature", 2: "kronecker"}.get(int(g.GetStat("last_path")), "?")
-        row = {"config": name, "workload": WORKLOADS[name], "path": path, "kernel": kernel_name(g, path), "ms_per_call": ms, "steps": steps,
+        hybrid = path == "kronecker" and form == "L2PROJECTION"       # matrix by the separable path, load vector by a quadrature kernel
+        row = {"config": name, "workload": WORKLOADS[name], "path": path, "kernel": kernel_name(g, path) + (" + " + kernel_name(g, "quadrature") if hybrid else ""), "ms_per_call": ms, "steps": steps,
                "launches_per_call": (g.GetStat("launches") - l0) / steps, "elements": nel, "nnz": nnz,
                "elements_per_s": nel / (ms * 1e-3), "value": (nnz / (ms * 1e-3) / 1e6) if nnz else None, "unit": "Mnnz/s"}
         bytes_alg = 8.0 * (nnz + nvec * (1 + (2 if state else 0))) + (8.0 * 3 * g.info()["nnp"][0] * g.info()["nnp"][1] * g.info()["nnp"][2] if case.geometry else 0.0)
         hb = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "algorithmic_bytes": bytes_alg}
         hb["frac"] = hb["achieved"] / hb["peak"]
-        if path == "kronecker" and form != "L2PROJECTION":
+        if path == "kronecker":      # write-once matrix (+ the small load-vector kernel of the hybrid case): HBM bound
             row["roofline"] = hb
         else:
             fl = g.GetStat("last_flops")
@@ -508,7 +509,10 @@ WORKLOADS = {
 def kernel_name(g, path):
     if path == "kronecker":
         return "kron_rows_kernel"
-    return {0: "quad_sf_kernel", 1: "quad_kernel", 2: "quad_gen_kernel", 3: "quad_sf3_kernel (+ sf3_geom_kernel)"}.get(int(g.GetStat("last_impl")), "?")
+    impl = int(g.GetStat("last_impl"))
+    if impl == 3:
+        return ("quad_sf3r_kernel" if int(g.GetStat("last_sf3_variant")) == 0 else "quad_sf3_kernel") + " (+ sf3_geom_kernel)"
+    return {0: "quad_sf_kernel", 1: "quad_kernel", 2: "quad_gen_kernel", 4: "quad_vec3_kernel"}.get(impl, "?")
 
 
 def _bc_struct(case):

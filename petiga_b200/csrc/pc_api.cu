@@ -705,7 +705,12 @@ int petiga_cuda_compute_ext(petiga_cuda_plan* P, int slot, int block, double shi
   if (need_gen) { impl = 2; rc = launch_quadrature_gen(P, kp); }
   else {
     rc = PETIGA_CUDA_ERR_SUP;
-    if (impl < 0 || impl == 3) {   // third-generation kernel where it applies (3-D, p = 3, dof 1, constant-coefficient linear forms)
+    if (impl < 0 && kp.mc1 == kp.mc0) {   // no matrix to integrate (IGAComputeVector, or the separable path has written it): vector kernel
+      rc = launch_quadrature_vec3(P, kp);
+      if (rc == 0) impl = 4;
+      else if (rc != PETIGA_CUDA_ERR_SUP) return rc;
+    }
+    if (rc == PETIGA_CUDA_ERR_SUP && (impl < 0 || impl == 3)) {   // third-generation kernel where it applies (3-D, p = 3, dof 1, constant-coefficient linear forms)
       rc = launch_quadrature_sf3(P, kp);
       if (rc == 0) impl = 3;
       else if (rc != PETIGA_CUDA_ERR_SUP || impl == 3) return rc;

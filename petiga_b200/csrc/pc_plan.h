@@ -103,6 +103,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // quadrature path (pc_quad.cu)
 int launch_quadrature(petiga_cuda_plan* P, const KParams& base);      // v1: pair loop as one register-tiled contraction
 int launch_quadrature_sf(petiga_cuda_plan* P, const KParams& base);   // v2: sum-factorised
+int launch_quadrature_vec3(petiga_cuda_plan* P, const KParams& base); // vector-only sum factorisation (3-D, dof 1, p = 2..4)
 int launch_quadrature_sf3(petiga_cuda_plan* P, const KParams& base);  // v3: persistent, warp-specialised, DMMA (3-D, p = 3, dof 1)
 int launch_quadrature_gen(petiga_cuda_plan* P, const KParams& base);  // generic runtime-degree kernel (pc_quadg.cu); also the face mode
 // separable path (pc_kron.cu)

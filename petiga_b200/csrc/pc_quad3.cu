@@ -5,8 +5,51 @@
 
 #include "pc_plan.h"
 #include "pc_quad3r.cuh"
+#include "pc_quadv.cuh"
 
 namespace pc {
+
+// vector-only assembly (pc_quadv.cuh): IGAComputeVector, or the load vector of a system whose matrix the separable path has written
+int launch_quadrature_vec3(petiga_cuda_plan* Pl, const KParams& base) {
+  const int dim = base.dim, dof = base.dof;
+  auto nope = [](const char* why) { set_error(std::string("quad_vec3: ") + why); return PETIGA_CUDA_ERR_SUP; };
+  if (dim != 3 || dof != 1) return nope("3-D, one dof per node only");
+  const int p = base.ax[0].p;
+  if (p < 2 || p > 4) return nope("degree 2..4 only");
+  for (int d = 0; d < 3; d++) if (base.ax[d].p != p || base.ax[d].nqp != p + 1) return nope("one degree on all axes with the default rule only");
+  if (base.Wt) return nope("rational geometry");
+  if (base.mc1 != base.mc0) return nope("vector-only");
+  if (base.slot != PETIGA_SLOT_VECTOR && !(base.slot == PETIGA_SLOT_SYSTEM && !base.any_bc)) return nope("IGAComputeVector or an unconstrained system only");
+  FormInfo fi = form_info(base.form, base.slot, dim, dof);
+  if (!fi.valid || fi.order > 1 || fi.needs_state || base.U) return nope("first-order forms without state only");
+  const int NV = base.vc1 - base.vc0;
+  if (NV <= 0 || NV > 4) return nope("components");
+  SF3Params sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.k = base;
+  std::vector<double> fv((size_t)NV, 0.0);
+  {
+    QPoint q;
+    memset(&q, 0, sizeof(q));
+    form_coefficients<3, 1>(base.form, base.slot, base.prm, base.shift, base.t, q, 0, NV, nullptr, fv.data());
+  }
+  for (int k = 0; k < NV; k++) sp.fconst[k] = fv[k];
+  std::vector<char> cpat(1, 0);
+  if (build_sf_lists(base, fi, base.X != nullptr, false, false, false, cpat, 0, sp.l)) return nope("component lists");
+  if (sp.l.NT > 4) return nope("too many tensor components");
+  for (int t = 0; t < sp.l.NT; t++) for (int d = 0; d < 3; d++) if (sp.l.torder[t][d] > 1) return nope("second derivatives");
+  sp.want_vec = 1;
+  if (base.nelem <= 0) return 0;
+  const int n3 = (p + 1) * (p + 1) * (p + 1), threads = (n3 + 31) / 32 * 32;
+  if (p == 2) quad_vec3_kernel<2><<<base.nelem, threads, 0, Pl->stream>>>(sp);
+  else if (p == 3) quad_vec3_kernel<3><<<base.nelem, threads, 0, Pl->stream>>>(sp);
+  else quad_vec3_kernel<4><<<base.nelem, threads, 0, Pl->stream>>>(sp);
+  PC_CUDA(cudaGetLastError());
+  Pl->launches++;
+  const double n4 = (double)(p + 1) * (p + 1) * (p + 1) * (p + 1);
+  Pl->last_flops = (double)base.nelem * ((base.X ? 2.0 * n4 * (6 + 9 + 12) : 0.0) + 2.0 * n4 * 3 * sp.l.NT + 60.0 * n3);
+  return 0;
+}
 
 int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
   const int dim = base.dim, dof = base.dof;

@@ -95,7 +95,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // Dirichlet value / Neumann load of local node (a0,a1,a2) of element ID (dof = 1): BuildFix / AddFixa / AddFlux, petigaelem.c:1166-1283
-__device__ __forceinline__ void sf3_node_bc(const KParams& prm, const int ID[3], const int ai[3], int gidx, int& onfix, double& vfix, double& vflux) {
+__device__ __forceinline__ void sf3_node_bc(const KParams& prm, const int ID[3], const int ai[3], int gidx, int& onfix, double& vfix, double& vflux, int pdeg = 3) {
   onfix = 0; vfix = 0.0; vflux = 0.0;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
@@ -104,11 +104,11 @@ __device__ __forceinline__ void sf3_node_bc(const KParams& prm, const int ID[3],
       const FixSide& fs = prm.bc[d][s];
       if (!(fs.vcount || fs.lcount)) continue;
       if (ID[d] != (s ? prm.ax[d].nel - 1 : 0)) continue;
-      if (ai[d] != (s ? 3 : 0)) continue;
+      if (ai[d] != (s ? pdeg : 0)) continue;
       for (int k = 0; k < fs.vcount; k++) if (fs.vfield[k] == 0) { onfix = 1; vfix = prm.fixtable ? prm.fixtable[gidx] : fs.vvalue[k]; }
       if (fs.lcount) {
         double A = 1.0;
-        for (int e = 0; e < 3; e++) if (e != d) A *= prm.ax[e].detJac[ID[e]] / 4.0;
+        for (int e = 0; e < 3; e++) if (e != d) A *= prm.ax[e].detJac[ID[e]] / (double)(pdeg + 1);   // detJac / nen (petigaelem.c:1139)
         if (prm.face_dS[d][s]) {
           const int f0 = (d == 0) ? 1 : 0, f1 = (d == 2) ? 1 : 2;
           A *= prm.face_dS[d][s][(ID[f0] - prm.ax[f0].es) + prm.ax[f0].ew * (ID[f1] - prm.ax[f1].es)];
