@@ -29,6 +29,7 @@ namespace {
 constexpr int kMaxTerms = 40;
 constexpr int kKronP = 4;               // the separable path keeps its pencil tables in static shared memory: degree <= 4
 constexpr int kMaxWW = (2 * kKronP + 1) * (2 * kKronP + 1);
+constexpr int kStageCap = 1218;         // dof > 1: doubles of dynamic shared memory per warp (one p = 2 BAIJ row of 125 3x3 blocks + its coefficients)
 
 struct KronTerm { unsigned char ij, rs0, rs1, rs2; double c; };
 struct KronVTerm { unsigned char i, r0, r1, r2; double c; };
@@ -53,6 +54,10 @@ struct KronParams {
   int nterms, nvterms, rsmask0;
   int fast_lo, fast_hi;   // axis-0 local row range [lo,hi) of full-width, storage-ordered, unconstrained rows (multiple of 4 long)
   int rsmask_ij[9];       // per (i,j) block: which axis-0 order pairs occur
+  int ncombo;             // distinct (axis-0 order pair, block entry) combinations; terms are sorted by combination
+  unsigned char combo_rs0[36], combo_ij[36], combo_first[37];
+  signed char slotA[9], slotB[9];   // ... as (at most) two order-pair indices per block entry, -1 = none; two_slot = 0 when an entry has more
+  int two_slot;
   KronTerm terms[kMaxTerms];
   KronVTerm vterms[8];
   FixSide bc[3][2];
@@ -149,7 +154,8 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 // row in storage order, so every store instruction writes 256 contiguous bytes.
 // PF > 0: all axes have degree PF, so a full-width interior row has compile-time extents and its loop unrolls completely
 template <int DOF, int PF>
-__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(const __grid_constant__ KronParams kp) {
+__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(const __grid_constant__ KronParams kp) {
+  extern __shared__ __align__(16) double dynstage[];   // dof > 1: kStageCap doubles per warp
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
   __shared__ int jkp1[kMaxWW];
@@ -157,25 +163,35 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
   __shared__ double Gm[2][kMaxWW];               // DOF == 1: G0/G3 with the Dirichlet (j,k) columns zeroed; Hs = sum over those columns of G*value
   __shared__ double Hs[2];
   __shared__ int fast_ctr;                       // next 4-row pass of the interior stretch (dynamic hand-out)               // DOF == 1: Dirichlet value of a column fixed by a j or k face (jkinfo bit 5)
-  __shared__ double stage[(DOF > 1) ? 8 * 32 * DOF * DOF : 1];
   const int pencil = (int)blockIdx.x;
   const int Aj = kp.ls[1] + pencil % kp.lw[1], Ak = kp.ls[2] + pencil / kp.lw[1];
   const int gj = Aj - kp.gs[1], gk = Ak - kp.gs[2];
   const int Wj = kp.Wg[1][gj], Wk = kp.Wg[2][gk], Wjk = Wj * Wk;
   const int fj = kp.first[1][Aj], fk = kp.first[2][Ak];
   const bool fixing = kp.any_bc && kp.slot == PETIGA_SLOT_SYSTEM;
+  // pencil tables: the 1-D rows of axes 1 and 2 first (one global load per thread), then one thread per (combination, column):
+  // a pencil's prologue used to be 25-49 threads walking all terms with two dependent global loads each (27 terms for
+  // elasticity: ~10 000 cycles per CTA, two thirds of a cfg-4 CTA's life)
+  __shared__ double sM[2][4][kMaxW];
+  for (int t = threadIdx.x; t < 2 * 4 * kMaxW; t += blockDim.x) {
+    const int d = t / (4 * kMaxW), rs = (t / kMaxW) & 3, cc = t % kMaxW;
+    (&sM[0][0][0])[t] = kp.M[1 + d][((size_t)rs * kp.nnp[1 + d] + (d ? Ak : Aj)) * kMaxW + cc];
+  }
   for (int t = threadIdx.x; t < 4 * DOF * DOF * kMaxWW; t += blockDim.x) (&G[0][0][0])[t] = 0.0;
   if (threadIdx.x == 0) fast_ctr = 0;
   __syncthreads();
+  for (int w = threadIdx.x; w < kp.ncombo * Wjk; w += blockDim.x) {
+    const int k = w / Wjk, t = w - k * Wjk, cj = t % Wj, ck = t / Wj;
+    double acc = 0.0;
+    for (int n = kp.combo_first[k]; n < kp.combo_first[k + 1]; n++) {
+      const KronTerm tm = kp.terms[n];
+      acc += tm.c * sM[0][tm.rs1][cj] * sM[1][tm.rs2][ck];
+    }
+    G[kp.combo_rs0[k]][kp.combo_ij[k]][t] = acc;
+  }
   bool jk_boundary = false;
   for (int t = threadIdx.x; t < Wjk; t += blockDim.x) {
     const int cj = t % Wj, ck = t / Wj;
-    for (int n = 0; n < kp.nterms; n++) {
-      const KronTerm tm = kp.terms[n];
-      const double mj = kp.M[1][((size_t)tm.rs1 * kp.nnp[1] + Aj) * kMaxW + cj];
-      const double mk = kp.M[2][((size_t)tm.rs2 * kp.nnp[2] + Ak) * kMaxW + ck];
-      G[tm.rs0][tm.ij][t] += tm.c * mj * mk;
-    }
     int info = bcode(fj + cj, kp.nnp[1], kp.periodic[1]) | (bcode(fk + ck, kp.nnp[2], kp.periodic[2]) << 2);
     if (cj == Aj - fj && ck == Ak - fk) info |= 16;
     int p1 = 0;
@@ -196,7 +212,9 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
     jkp1[t] = p1;
   }
   // does any column of this pencil touch a (j,k) boundary face?  (uniform over the CTA)
-  jk_boundary = fixing && ((!kp.periodic[1] && (fj == 0 || fj + Wj == kp.nnp[1])) || (!kp.periodic[2] && (fk == 0 || fk + Wk == kp.nnp[2])));
+  // (only faces that carry Dirichlet values matter: cfg 4 constrains the two axis-0 faces only)
+  jk_boundary = fixing && ((!kp.periodic[1] && ((fj == 0 && kp.bc[1][0].vcount) || (fj + Wj == kp.nnp[1] && kp.bc[1][1].vcount))) ||
+                           (!kp.periodic[2] && ((fk == 0 && kp.bc[2][0].vcount) || (fk + Wk == kp.nnp[2] && kp.bc[2][1].vcount))));
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool want_mat = kp.values != nullptr, want_vec = kp.rhs != nullptr;
@@ -251,10 +269,44 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
       nfast = kp.fast_hi - fast_lo;
     }
   }
+  // ---- dof > 1: a lane owns one (j,k) column offset of the pencil and keeps its G values in REGISTERS for all rows of the pencil
+  //      (G does not depend on the axis-0 row); a row is built in shared memory in storage order and written with full-width
+  //      warp stores.  Was: 18 shared-memory loads per block in every row + a 288-double staging round trip per 30 blocks
+  //      (cfg 4: 2.63 ms = 47 % of the HBM rate). ----
+  constexpr int DD = DOF * DOF;
+  bool blk_fast = false;
+  double gA[DD], gB[DD];
+  if constexpr (DOF > 1 && PF > 0) {
+    constexpr int WIC = 2 * PF + 1;
+    const bool row_jk_bc = fixing && ((rcj && (kp.bc[1][rcj - 1].vcount || kp.bc[1][rcj - 1].lcount)) || (rck && (kp.bc[2][rck - 1].vcount || kp.bc[2][rck - 1].lcount)));
+    blk_fast = want_mat && kp.two_slot && kp.dim == 3 && simple_jk && !jk_boundary && !row_jk_bc && Wjk == WIC * WIC && WiF == WIC &&
+               WIC * WIC <= 32 && ((WIC * WIC * WIC * DD + 2) & ~1) + WIC * DD * 2 <= kStageCap;
+    if (blk_fast) {
+#pragma unroll
+      for (int ij = 0; ij < DD; ij++) {
+        gA[ij] = (lane < Wjk && kp.slotA[ij] >= 0) ? G[kp.slotA[ij]][ij][lane] : 0.0;
+        gB[ij] = (lane < Wjk && kp.slotB[ij] >= 0) ? G[kp.slotB[ij]][ij][lane] : 0.0;
+      }
+    }
+  }
   const int nslow = lw0 - nfast;   // the general loop walks the remaining rows (compacted index)
   // per-row parameters are prefetched one row ahead (registers), so that their L2 latency overlaps the stores of the
   // current row instead of stalling every row (ncu r1_ncu_kron_rows_mesh128_v3: long_scoreboard was the top stall)
-  struct RowP { int Wi, fi, simple; int64_t base; double a0, a3; };
+  constexpr int NAC = (DOF > 1 && PF > 0) ? ((2 * PF + 1) * DD * 2 + 31) / 32 : 1;   // dof > 1 fast path: this lane's axis-0 factors of a row
+  int acoff[NAC];
+#pragma unroll
+  for (int k = 0; k < NAC; k++) {
+    acoff[k] = -1;
+    if (DOF > 1 && PF > 0) {
+      const int t = lane + 32 * k;
+      if (t < (2 * PF + 1) * DD * 2) {
+        const int ci = t / (DD * 2), r2 = t - ci * (DD * 2), ij = r2 >> 1;
+        const int rs = (r2 & 1) ? kp.slotB[ij] : kp.slotA[ij];
+        if (rs >= 0) acoff[k] = rs * nnp0 * kMaxW + ci;
+      }
+    }
+  }
+  struct RowP { int Wi, fi, simple; int64_t base; double a0, a3; double acv[NAC]; };
   auto load_row = [&](int il_) {
     RowP r;
     const int Ai_ = ls0 + il_, gi_ = Ai_ - gs0;
@@ -262,9 +314,13 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
     r.base = __ldg(rowbase + il_ + lr0);
     r.a0 = r.a3 = 0.0;
     if (DOF == 1) { r.a0 = __ldg(M0 + (size_t)Ai_ * kMaxW + ciF); r.a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai_) * kMaxW + ciF); }   // only the scalar fast paths use them
+#pragma unroll
+    for (int k = 0; k < NAC; k++) r.acv[k] = (DOF > 1 && PF > 0 && blk_fast && acoff[k] >= 0) ? __ldg(M0 + acoff[k] + (size_t)Ai_ * kMaxW) : 0.0;
     return r;
   };
-  RowP cur = {0, 0, 0, 0, 0.0, 0.0}, nxt = cur;
+  RowP cur, nxt;
+  memset(&cur, 0, sizeof(cur));
+  nxt = cur;
   auto row_of = [&](int idx) { return (idx < fast_lo || nfast == 0) ? idx : idx + nfast; };
   if (warp < nslow) cur = load_row(row_of(warp));
   for (int idx = warp; idx < nslow; idx += nwarps, cur = nxt) {
@@ -275,6 +331,74 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
     const int lr = il + lr0;
     const int64_t base = cur.base;
     const bool SIMPLE = simple_jk && cur.simple;
+    if constexpr (DOF > 1 && PF > 0) {
+      if (blk_fast && SIMPLE && Wi == WiF && !(fixing && !per0 && (Ai == 0 || Ai == nnp0 - 1 || fi == 0 || fi + Wi == nnp0))) {
+        constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, WR = WIC * WJKC, NV = WR * DD;       // all extents static: fully unrolled
+        double* stg0 = dynstage + warp * kStageCap;
+        double* ac = stg0 + ((NV + 2) & ~1);                           // ac[ci][ij][2]: the row's axis-0 factors of the two order pairs
+        const int al = (int)((base * DD) & 1);                         // stage with the parity of the destination: 16-byte stores line up
+        double* stg = stg0 + al;
+#pragma unroll
+        for (int k = 0; k < NAC; k++) {
+          const int t = lane + 32 * k;
+          if (t < WIC * DD * 2) ac[t] = cur.acv[k];                   // loaded one row ahead with the row parameters
+        }
+        __syncwarp();
+        if (lane < WJKC) {
+          if (kp.block) {
+#pragma unroll
+            for (int ci = 0; ci < WIC; ci++) {
+              double* o = stg + (lane * WIC + ci) * DD;
+#pragma unroll
+              for (int ij = 0; ij < DD; ij++) {
+                const double2 a2 = *reinterpret_cast<const double2*>(ac + (ci * DD + ij) * 2);
+                o[(ij % DOF) * DOF + ij / DOF] = fma(a2.y, gB[ij], a2.x * gA[ij]);      // column-major block
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ci = 0; ci < WIC; ci++) {
+              double* o = stg + (lane * WIC + ci) * DOF;
+#pragma unroll
+              for (int ij = 0; ij < DD; ij++) {
+                const double2 a2 = *reinterpret_cast<const double2*>(ac + (ci * DD + ij) * 2);
+                o[(ij / DOF) * WR * DOF + ij % DOF] = fma(a2.y, gB[ij], a2.x * gA[ij]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        double* __restrict__ dst = values + (size_t)base * DD;
+        if (al && lane == 0) dst[0] = stg[0];                          // head element of an odd row start
+        {
+          const double2* __restrict__ s2 = reinterpret_cast<const double2*>(stg + al);
+          double2* __restrict__ d2 = reinterpret_cast<double2*>(dst + al);
+          constexpr int NP = (NV - 1) / 2;                             // pairs that exist for either parity
+#pragma unroll
+          for (int k = 0; k < (NP + 31) / 32; k++) {
+            const int t = lane + 32 * k;
+            if (t < NP) d2[t] = s2[t];
+          }
+          // tail: NV - al - 2 NP elements (0, 1 or 2) after the pairs
+          const int done = al + 2 * NP;
+          if (lane < NV - done) dst[done + lane] = stg[done + lane];
+        }
+        __syncwarp();
+        if (want_vec && lane == 0) {
+#pragma unroll
+          for (int cc = 0; cc < DOF; cc++) {
+            double F = 0.0;
+            for (int n = 0; n < kp.nvterms; n++) {
+              const KronVTerm vt = kp.vterms[n];
+              if (vt.i != cc) continue;
+              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+            }
+            rhs[(size_t)lr * DOF + cc] = F;
+          }
+        }
+        continue;
+      }
+    }
     if (fast_ok) {
       const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
@@ -459,7 +583,7 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 3) kron_rows_kernel(cons
       // BAIJ blocks of the ngrp*Wi entries a warp produces per iteration are contiguous in memory when the row is in
       // storage order: stage them in shared memory and write them back with full 256-byte warp stores
       const bool staged = (DOF > 1) && want_mat && kp.block && SIMPLE;
-      double* stg = (DOF > 1) ? &stage[(threadIdx.x >> 5) * 32 * DOF * DOF] : nullptr;
+      double* stg = (DOF > 1) ? dynstage + (threadIdx.x >> 5) * kStageCap : nullptr;
       for (int cjk0 = 0; cjk0 < Wjk; cjk0 += ngrp) {
         const int cjk = cjk0 + grp;
         const bool act = grp < ngrp && cjk < Wjk;
@@ -671,9 +795,12 @@ static int launch_kron_kernel(petiga_cuda_plan* P, const KronParams& kp) {
   if (const char* e = getenv("PETIGA_KRON_THREADS")) threads = std::max(32, std::min(256, atoi(e) / 32 * 32));   // tuning knob
   int pf = L.ax[0].p;
   for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
-  if (L.dim < 3 || L.dof != 1) pf = 0;
-#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) kron_rows_kernel<DOF_, PF_><<<blocks, threads, 0, P->stream>>>(kp);
-  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0)
+  if (L.dim < 3 || (L.dof != 1 && pf > 2)) pf = 0;
+  const size_t dyn = L.dof > 1 ? (size_t)(threads / 32) * kStageCap * sizeof(double) : 0;
+#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) { \
+    if (dyn) PC_CUDA(cudaFuncSetAttribute(kron_rows_kernel<DOF_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    kron_rows_kernel<DOF_, PF_><<<blocks, threads, dyn, P->stream>>>(kp); }
+  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0) KL(2, 1) KL(2, 2) KL(3, 1) KL(3, 2)
 #undef KL
   PC_CUDA(cudaGetLastError());
   P->launches++;
@@ -749,6 +876,25 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
   HT(1, 1) HT(1, 2) HT(1, 3) HT(2, 1) HT(2, 2) HT(2, 3) HT(3, 1) HT(3, 2) HT(3, 3)
 #undef HT
   if (kp.nterms > kMaxTerms || kp.nvterms > 8) { set_error("separable path: too many coefficient terms"); return PETIGA_CUDA_ERR_SUP; }
+  {  // terms grouped by (axis-0 order pair, block entry), original order kept inside a group (same summation order as before)
+    std::stable_sort(kp.terms, kp.terms + kp.nterms, [](const KronTerm& a, const KronTerm& b) { return a.rs0 * 16 + a.ij < b.rs0 * 16 + b.ij; });
+    kp.ncombo = 0;
+    for (int n = 0; n < kp.nterms; n++) {
+      if (n == 0 || kp.terms[n].rs0 != kp.terms[n - 1].rs0 || kp.terms[n].ij != kp.terms[n - 1].ij) {
+        kp.combo_rs0[kp.ncombo] = kp.terms[n].rs0; kp.combo_ij[kp.ncombo] = kp.terms[n].ij; kp.combo_first[kp.ncombo] = (unsigned char)n;
+        kp.ncombo++;
+      }
+    }
+    kp.combo_first[kp.ncombo] = (unsigned char)kp.nterms;
+  }
+  kp.two_slot = 1;
+  for (int ij = 0; ij < 9; ij++) {
+    kp.slotA[ij] = kp.slotB[ij] = -1;
+    int n = 0;
+    for (int rs = 0; rs < 4; rs++)
+      if ((kp.rsmask_ij[ij] >> rs) & 1) { if (n == 0) kp.slotA[ij] = (signed char)rs; else if (n == 1) kp.slotB[ij] = (signed char)rs; n++; }
+    if (n > 2) kp.two_slot = 0;
+  }
   if (slot == PETIGA_SLOT_SYSTEM && P->has_bc)
     for (int d = 0; d < L.dim; d++)
       for (int s = 0; s < 2; s++) {

@@ -163,7 +163,7 @@ def test_hot_kernel_register_budget():
     assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4ELi1") <= 85
     assert regs("pc_quad2.ptxas.log", "quad_sf_kernelILi3ELi3ELi1ELi4ELi4") <= 64
     assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi1ELi3") <= 64
-    assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi3ELi0") <= 85      # cfg 4 (BAIJ bs=3): 3 CTAs per SM; 122 registers cost 43 %
+    assert regs("pc_kron.ptxas.log", "kron_rows_kernelILi3ELi0") <= 128     # cfg 4 (BAIJ bs=3): 2 CTAs per SM (each warp stages a whole row in shared memory)
 
 
 def test_functional_and_boundary_form_argument_checks():
