@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-quad", action="store_true")
+    ap.add_argument("--no-solve", action="store_true", help="skip the assemble + device CG solve figure (e2e_solve)")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity cases run before the timed region")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations (N=1 only)")
     args = ap.parse_args()
@@ -327,6 +328,36 @@ def main():
                "h2d_bytes_per_step": C.sizeof(bc), "d2h_bytes_per_step": (nval + nvec) * 8, "steps": ksteps, "rhs_checksum8": chk}
         L.petiga_cuda_host_free(hv); L.petiga_cuda_host_free(hr)
 
+    # -------- assemble + solve with the matrix never leaving the device: IGAComputeSystem, then CG + Jacobi on the
+    #          device CSR (IGACreateKSP / KSPSolve of the host mirror), then ONLY the solution vector goes to the host --------
+    e2e_solve = None
+    if not args.no_solve and args.geometry == "identity":
+        X = g.CreateVec()
+        with torch.cuda.stream(stream):
+            g.SetOption("path", 0)
+            g.ComputeSystem(A, B)
+            g.Solve(A, B, X, rtol=1e-8, maxits=20)                # warm-up: allocations, NCCL channels
+            barrier()
+            e0.record(stream)
+            g.ComputeSystem(A, B)
+            em = torch.cuda.Event(enable_timing=True)
+            em.record(stream)
+            its, rel = g.Solve(A, B, X, rtol=1e-8, maxits=5000)
+            xh = X.get()                                           # device -> host: the solution, nothing else
+            e1.record(stream)
+            barrier()
+        t_all = torch.tensor([e0.elapsed_time(e1), em.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        e2e_solve = {"ms": float(t_all[0]), "solve_ms": float(t_all[1]), "cg_iterations": int(its), "relative_residual": float(rel),
+                     "rtol": 1e-8, "preconditioner": "jacobi", "d2h_bytes": int(nvec_local * 8), "h2d_bytes": 0, "matrix_bytes_over_pcie": 0,
+                     "ms_per_iteration": float(t_all[1]) / max(int(its), 1),
+                     "spmv_GBps_per_gpu": 12.0 * nnz_local / (float(t_all[1]) / max(int(its), 1) * 1e-3) / 1e9,
+                     "solution_checksum": float(np.abs(xh).sum()),
+                     "note": "IGAComputeSystem + KSPSolve (CG, Jacobi) with the CSR consumed in place on the device; spmv_GBps counts 12 B per nonzero "
+                             "(value + column index) over the whole iteration time (SpMV + 2 dot products + 2 vector updates)"}
+        X.destroy()
+
     # -------- the other BASELINE configurations, one GPU, device-resident (secondary rows of SURVEY 8d) --------
     configs = None
     if world == 1 and not args.no_configs and args.mesh == 128 and args.geometry == "identity":
@@ -395,6 +426,8 @@ def main():
                                                         "red.global.add.f64 rate and shared-memory bandwidth (DESIGN.md 3.2b), not the FP64 pipe"}}
     if e2e:
         line["e2e"] = e2e
+    if e2e_solve:
+        line["e2e_solve"] = e2e_solve
     if parity is not None:
         line["parity"] = parity
     if configs is not None:

@@ -200,6 +200,19 @@ int petiga_cuda_compute_ext(petiga_cuda_plan *plan, int slot, int block, double 
                             const double *U, double shift2, const double *W, double t0, double *values, double *rhs);
 int petiga_cuda_finish(petiga_cuda_plan *plan);
 
+/* ---- the step after the path: device-resident consumers of the assembled CSR ----
+   In the reference the assembled Mat goes to PETSc: IGACreateKSP (src/petiga.c:856-885), KSPSetOperators + KSPSolve
+   (demo/Poisson3D.c:73-83; the demo targets run -ksp_type cg -pc_type jacobi).  These two entry points keep that step on the
+   device, so that assemble + solve moves no matrix byte over PCIe.  `block` and `values` as in petiga_cuda_compute; x, y, b are
+   device vectors of the owned rows (nown * dof).  Multi-rank plans gather the operand over NCCL (rank-major global numbering).
+   petiga_cuda_spmv      <- MatMult
+   petiga_cuda_solve_cg  <- KSPSolve with KSPCG + PCJACOBI: x is the initial guess on entry; stops at |r| <= max(rtol |b|, atol)
+                            or maxit; *iters and *relres (= |r| / |b|) report the outcome.  The matrix must be symmetric positive
+                            definite (Poisson, Laplace, mass, elasticity systems). */
+int petiga_cuda_spmv(petiga_cuda_plan *plan, int block, const double *values, const double *x, double *y);
+int petiga_cuda_solve_cg(petiga_cuda_plan *plan, int block, const double *values, const double *b, double *x,
+                         double rtol, double atol, int maxit, int *iters, double *relres);
+
 /* IGAComputeScalar (src/petigacomp.c:35-96): S[k] = sum over all ranks, elements and quadrature points of
    detJac*weight * Scalar_k(point, U).  U: device [owned nodes * dof] or NULL (a NULL state evaluates as zero, which is how
    IGAComputeErrorNorm(iga,k,NULL,Exact,..) yields the norms of the exact solution).  S_host receives the n global sums on
@@ -218,6 +231,7 @@ int petiga_cuda_malloc(void **ptr, size_t bytes);
 int petiga_cuda_free(void *ptr);
 int petiga_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int petiga_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int petiga_cuda_memset(void *dst, int value, size_t bytes);
 int petiga_cuda_host_alloc(void **ptr, size_t bytes);   /* pinned */
 int petiga_cuda_host_free(void *ptr);
 /* sum (a-b)^2 and sum b^2 over n device doubles on the current device (deterministic; synchronous): lets a caller compare two

@@ -39,6 +39,7 @@ typedef int PetscBool;
 #define PETSC_ERR_SUP 56
 #define PETSC_ERR_ORDER 58
 #define PETSC_ERR_ARG_OUTOFRANGE 63
+#define PETSC_ERR_ARG_IDN 61
 #define PETSC_ERR_ARG_WRONG 62
 #define PETSC_ERR_ARG_WRONGSTATE 73
 #define PETSC_ERR_LIB 76
@@ -56,6 +57,7 @@ typedef struct _n_IGAAxis *IGAAxis;
 typedef struct _n_IGAPoint *IGAPoint;       /* opaque here: forms run on the device */
 typedef struct _n_IGAForm *IGAForm;         /* include/petiga.h:220-268; opaque handle of the IGA's form */
 typedef struct _p_Mat *Mat;
+typedef struct _p_KSP *KSP;
 typedef struct _p_Vec *Vec;
 
 /* callback signatures of include/petiga.h:153-171 */
@@ -237,6 +239,19 @@ PetscErrorCode IGASetOption(IGA iga, const char *name, PetscReal value);     /* 
                                                                                  IGACompute* only enqueue on the IGA's stream (device-
                                                                                  resident hand-off to a GPU solve) */
 PetscErrorCode IGAGetStat(IGA iga, const char *name, PetscReal *value);
+/* ---- the step after the path: the assembled Mat stays on the device and is consumed there ----
+   IGACreateKSP: src/petiga.c:856-885; use as demo/Poisson3D.c:73-83 does.  The solver is conjugate gradients with the Jacobi
+   diagonal (-ksp_type cg -pc_type jacobi), for the symmetric positive definite systems of the linear demos; KSPGetResidualNorm
+   returns |r| / |b|.  MatMult is the product the solver iterates with. */
+PetscErrorCode MatMult(Mat A, Vec x, Vec y);
+PetscErrorCode IGACreateKSP(IGA iga, KSP *ksp);
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P);
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt maxits);
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x);
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its);
+PetscErrorCode KSPGetResidualNorm(KSP ksp, PetscReal *rnorm);
+PetscErrorCode KSPDestroy(KSP *ksp);
+
 PetscErrorCode IGASynchronize(IGA iga);                                        /* wait for the IGA's stream (after IGASetOption(iga,"async",1)) */
 PetscErrorCode IGASetStream(IGA iga, void *cuda_stream);                      /* stream all device work is enqueued on */
 void *IGAGetLayout(IGA iga);                                                 /* the petiga_layout behind the IGA */

@@ -49,6 +49,9 @@ struct _p_Vec {
 struct _p_Mat {
   IGA iga; int baij; int bs; int nrows; int64_t nnz; const int* d_rowptr; const int* d_colidx; double* d_values; long gen; };
 
+struct _p_KSP {      // IGACreateKSP: conjugate gradients + Jacobi on the device (petiga_cuda_solve_cg)
+  IGA iga; Mat A; double rtol, abstol; int maxits, its; double rnorm; };
+
 struct _p_IGA {
   IGAComm comm;
   int dim = -1, dof = -1, order = -1, setup = 0;
@@ -824,6 +827,54 @@ PetscErrorCode IGASynchronize(IGA g) {
   if (PetscErrorCode e = check(g)) return e;
   return g->plan ? from_cuda(petiga_cuda_finish(g->plan)) : 0;
 }
+
+// ---- the step after the path: MatMult and a KSP that stays on the device (src/petiga.c:856-885 IGACreateKSP; demo/Poisson3D.c:73-83) ----
+PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
+  if (!A || !x || !y) return fail(PETSC_ERR_ARG_NULL, "Null Mat/Vec");
+  if (PetscErrorCode e = check_owner(A, nullptr, "Mat")) return e;
+  if (PetscErrorCode e = check_owner(x, A->iga, "Vec")) return e;
+  if (PetscErrorCode e = check_owner(y, A->iga, "Vec")) return e;
+  if (x == y) return fail(PETSC_ERR_ARG_IDN, "x and y must be different vectors");
+  IGA g = A->iga;
+  if (int rc = petiga_cuda_spmv(g->plan, A->baij, A->d_values, x->d, y->d)) return from_cuda(rc);
+  return g->async ? 0 : from_cuda(petiga_cuda_finish(g->plan));
+}
+PetscErrorCode IGACreateKSP(IGA g, KSP* ksp) {
+  if (PetscErrorCode e = check(g)) return e;
+  if (!ksp) return fail(PETSC_ERR_ARG_NULL, "Null pointer");
+  if (!g->setup) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call IGASetUp() first");
+  *ksp = new _p_KSP{g, nullptr, 1e-5, 1e-50, 10000, 0, 0.0};      // PETSc's default tolerances (KSPSetTolerances man page)
+  return 0;
+}
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P) {
+  if (!ksp || !A) return fail(PETSC_ERR_ARG_NULL, "Null KSP/Mat");
+  if (P && P != A) return fail(PETSC_ERR_SUP, "KSPSetOperators: the preconditioner is the Jacobi diagonal of A; pass P = A");
+  if (PetscErrorCode e = check_owner(A, ksp->iga, "Mat")) return e;
+  ksp->A = A;
+  return 0;
+}
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt maxits) {
+  (void)dtol;
+  if (!ksp) return fail(PETSC_ERR_ARG_NULL, "Null KSP");
+  if (rtol < 0 || abstol < 0 || maxits < 0) return fail(PETSC_ERR_ARG_OUTOFRANGE, "Tolerances and iteration count must be nonnegative");
+  ksp->rtol = rtol; ksp->abstol = abstol; ksp->maxits = maxits;
+  return 0;
+}
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
+  if (!ksp || !b || !x) return fail(PETSC_ERR_ARG_NULL, "Null KSP/Vec");
+  if (!ksp->A) return fail(PETSC_ERR_ARG_WRONGSTATE, "Must call KSPSetOperators() first");
+  if (PetscErrorCode e = check_owner(ksp->A, ksp->iga, "Mat")) return e;
+  if (PetscErrorCode e = check_owner(b, ksp->iga, "Vec")) return e;
+  if (PetscErrorCode e = check_owner(x, ksp->iga, "Vec")) return e;
+  if (b == x) return fail(PETSC_ERR_ARG_IDN, "b and x must be different vectors");
+  IGA g = ksp->iga;
+  // KSPSolve starts from x = 0 unless KSPSetInitialGuessNonzero was called (not mirrored)
+  if (int rc = petiga_cuda_memset(x->d, 0, (size_t)x->n * sizeof(double))) return from_cuda(rc);
+  return from_cuda(petiga_cuda_solve_cg(g->plan, ksp->A->baij, ksp->A->d_values, b->d, x->d, ksp->rtol, ksp->abstol, ksp->maxits, &ksp->its, &ksp->rnorm));
+}
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt* its) { if (!ksp || !its) return fail(PETSC_ERR_ARG_NULL, "Null pointer"); *its = ksp->its; return 0; }
+PetscErrorCode KSPGetResidualNorm(KSP ksp, PetscReal* rnorm) { if (!ksp || !rnorm) return fail(PETSC_ERR_ARG_NULL, "Null pointer"); *rnorm = ksp->rnorm; return 0; }
+PetscErrorCode KSPDestroy(KSP* ksp) { if (ksp && *ksp) { delete *ksp; *ksp = nullptr; } return 0; }
 PetscErrorCode IGAComputeVector(IGA g, Vec B) { if (!B) return fail(PETSC_ERR_ARG_NULL, "Null Vec"); return run(g, PETIGA_SLOT_VECTOR, 0, nullptr, 0, nullptr, nullptr, B); }
 PetscErrorCode IGAComputeMatrix(IGA g, Mat A) { if (!A) return fail(PETSC_ERR_ARG_NULL, "Null Mat"); return run(g, PETIGA_SLOT_MATRIX, 0, nullptr, 0, nullptr, A, nullptr); }
 PetscErrorCode IGAComputeSystem(IGA g, Mat A, Vec B) { if (!A || !B) return fail(PETSC_ERR_ARG_NULL, "Null Mat/Vec"); return run(g, PETIGA_SLOT_SYSTEM, 0, nullptr, 0, nullptr, A, B); }

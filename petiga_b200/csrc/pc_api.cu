@@ -35,6 +35,7 @@ void nvtx_init() {
 }
 }  // namespace
 void nvtx_push(int slot) { nvtx_init(); if (g_nvtx_state == 1) g_nvtx_push(kSlotNames[slot]); }
+void nvtx_push(const char* name) { nvtx_init(); if (g_nvtx_state == 1) g_nvtx_push(name); }
 void nvtx_pop() { if (g_nvtx_state == 1) g_nvtx_pop(); }
 
 static thread_local std::string g_last_error;
@@ -340,7 +341,7 @@ int petiga_cuda_plan_destroy(petiga_cuda_plan* P) {
   for (void* d : P->allocs) cudaFree(d);
   for (int b = 0; b < 2; b++) { cudaFree(P->d_rowptr[b]); cudaFree(P->d_colidx[b]); }
   cudaFree(P->d_X); cudaFree(P->d_W); cudaFree(P->d_fixtable); cudaFree(P->d_ghost_values); cudaFree(P->d_recv);
-  cudaFree(P->d_scalar); cudaFree(P->d_sf3_dprime); cudaFree(P->d_values_own); cudaFree(P->d_rhs_own); cudaFree(P->d_U_own); cudaFree(P->d_V_own);
+  cudaFree(P->d_scalar); cudaFree(P->d_sf3_dprime); cudaFree(P->d_solve_work); cudaFree(P->d_solve_xfull); cudaFree(P->d_values_own); cudaFree(P->d_rhs_own); cudaFree(P->d_U_own); cudaFree(P->d_V_own);
   if (P->h_pinned) cudaFreeHost(P->h_pinned);
   if (P->ev0) cudaEventDestroy(P->ev0);
   if (P->ev1) cudaEventDestroy(P->ev1);
@@ -847,6 +848,7 @@ int petiga_cuda_malloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_
 int petiga_cuda_free(void* ptr) { PC_CUDA(cudaFree(ptr)); return 0; }
 int petiga_cuda_memcpy_h2d(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
 int petiga_cuda_memcpy_d2h(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int petiga_cuda_memset(void* dst, int value, size_t bytes) { PC_CUDA(cudaMemset(dst, value, bytes)); return 0; }
 int petiga_cuda_host_alloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1)); return 0; }
 int petiga_cuda_host_free(void* ptr) { PC_CUDA(cudaFreeHost(ptr)); return 0; }
 

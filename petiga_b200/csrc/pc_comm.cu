@@ -21,6 +21,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,7 +68,7 @@ int nccl_load() {
 #define LOADSYM(field, sym) *(void**)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) { set_error("missing NCCL symbol " sym); return PETIGA_CUDA_ERR_NCCL; }
   LOADSYM(GetUniqueId, "ncclGetUniqueId") LOADSYM(CommInitRank, "ncclCommInitRank") LOADSYM(CommDestroy, "ncclCommDestroy")
   LOADSYM(Send, "ncclSend") LOADSYM(Recv, "ncclRecv") LOADSYM(GroupStart, "ncclGroupStart") LOADSYM(GroupEnd, "ncclGroupEnd")
-  LOADSYM(GetErrorString, "ncclGetErrorString") LOADSYM(AllReduce, "ncclAllReduce")
+  LOADSYM(GetErrorString, "ncclGetErrorString") LOADSYM(AllReduce, "ncclAllReduce") LOADSYM(Broadcast, "ncclBroadcast")
 #undef LOADSYM
   g_nccl.handle = h;
   return 0;
@@ -89,6 +90,27 @@ int allreduce_sum(petiga_cuda_plan* P, double* d_buf, int n) {
   if (rc) return rc;
   PC_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)P->nccl, P->stream));
   P->launches += 1;
+  return 0;
+}
+
+// every rank's owned slice into a full-length vector in the global (rank-major) numbering: the operand gather of a distributed
+// matrix-vector product (VecScatter of MatMult_MPIAIJ); one grouped broadcast per owner, since the slices differ in length
+int allgather_owned(petiga_cuda_plan* P, const double* owned, double* full) {
+  const Layout& L = P->L;
+  if (!P->nccl) { set_error("multi-rank plan without an NCCL communicator"); return PETIGA_CUDA_ERR_ORDER; }
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclComm_t comm = (ncclComm_t)P->nccl;
+  ncclResult_t gr = g_nccl.GroupStart();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclGroupStart");
+  for (int r = 0; r < L.nranks && gr == ncclSuccess; r++) {
+    const size_t off = (size_t)L.rank_start[r] * L.dof, cnt = (size_t)(L.rank_start[r + 1] - L.rank_start[r]) * L.dof;
+    gr = g_nccl.Broadcast(r == L.rank ? owned : full + off, full + off, cnt, ncclDouble, r, comm, P->stream);
+  }
+  ncclResult_t ge = g_nccl.GroupEnd();
+  if (gr != ncclSuccess) return nccl_fail(gr, "ncclBroadcast (operand gather)");
+  if (ge != ncclSuccess) return nccl_fail(ge, "ncclGroupEnd");
+  P->launches++;
   return 0;
 }
 

@@ -35,6 +35,8 @@ struct petiga_cuda_plan {
   double* d_kronrow[3] = {nullptr, nullptr, nullptr};   // 1-D global banded matrices [4][nnp][kMaxW]
   double* d_sfpp[3] = {nullptr, nullptr, nullptr};      // pair-product tables of the sum-factorised kernel
   double* d_sf3pp[3] = {nullptr, nullptr, nullptr};     // the same products in the fragment layout of the third-generation kernel
+  double* d_solve_work = nullptr; size_t solve_work_cap = 0;     // pc_solve.cu: r, z, p, Ap, 1/diag, reduction partials, scalars
+  double* d_solve_xfull = nullptr; size_t solve_xfull_cap = 0;   // full-length operand of a distributed matrix-vector product
   double* d_sf3_dprime = nullptr; size_t sf3_dprime_cap = 0;   // D'[element][pair][64] of the geometry pre-pass (mapped geometry)
 
   // pattern (owned by the plan), per block mode
@@ -113,6 +115,9 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
 int exchange_ghost_rows(petiga_cuda_plan* P, int block, double* values, double* rhs, bool mat, bool vec);
 int halo_state(petiga_cuda_plan* P, const double* U_own, double* U_loc);
 int nccl_load();
+int allgather_owned(petiga_cuda_plan* P, const double* owned, double* full);
+int allreduce_sum(petiga_cuda_plan* P, double* d_buf, int n);
+void nvtx_push(const char* name);
 // boundary-integral pass (pc_bnd.cu)
 int launch_boundary_pass(petiga_cuda_plan* P, int slot, int form, const double* prm, double* rhs, bool apply_fix);
 }  // namespace pc

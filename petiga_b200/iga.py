@@ -428,6 +428,25 @@ class IGA:
     def SetStream(self, stream_ptr):
         _chk(self.H.IGASetStream(self.h, C.c_void_p(stream_ptr)))
 
+    def MatMult(self, A, x, y):
+        _chk(self.H.MatMult(A.h, x.h, y.h))
+
+    def Solve(self, A, b, x, rtol=1e-8, atol=1e-50, maxits=10000):
+        """IGACreateKSP + KSPSetOperators + KSPSetTolerances + KSPSolve (demo/Poisson3D.c:73-83) on the device: CG + Jacobi.
+        Returns (iterations, |r| / |b|)."""
+        ksp = C.c_void_p()
+        _chk(self.H.IGACreateKSP(self.h, C.byref(ksp)))
+        try:
+            _chk(self.H.KSPSetOperators(ksp, A.h, A.h))
+            _chk(self.H.KSPSetTolerances(ksp, C.c_double(rtol), C.c_double(atol), C.c_double(1e5), int(maxits)))
+            _chk(self.H.KSPSolve(ksp, b.h, x.h))
+            its, rn = C.c_int(), C.c_double()
+            _chk(self.H.KSPGetIterationNumber(ksp, C.byref(its)))
+            _chk(self.H.KSPGetResidualNorm(ksp, C.byref(rn)))
+            return its.value, rn.value
+        finally:
+            self.H.KSPDestroy(C.byref(ksp))
+
     def SetOption(self, name, value):
         _chk(self.H.IGASetOption(self.h, name.encode(), C.c_double(value)))
 

@@ -171,6 +171,39 @@ def main():
         nfail += int(flag.item() != 0)
         vU.destroy()
         g.Destroy()
+    # ---- the step after the path on several ranks: MatMult with the operand gathered over NCCL, CG + Jacobi (pc_solve.cu) ----
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    for name, case, form, prm in [("solve poisson3d", Case(3, p=2, N=(8, 7, 9), bcv=dall(3)), "POISSON", []),
+                                  ("solve elasticity3d", Case(3, dof=3, p=2, N=5, bcv=[(0, 0, c, 0.0) for c in range(3)] + [(0, 1, 0, 1.0)]), "ELASTICITY", [1.0, 1.0])]:
+        o = case.oracle()
+        o.setup()
+        rp, ci, rs = o.pattern(world)
+        Ko, Fo = o.assemble("SYSTEM", form, prm, size=world)
+        dof = case.dof
+        n = (len(rp) - 1) * dof
+        M = (sp.bsr_matrix((Ko.reshape(-1, dof, dof), ci, rp), shape=(n, n)) if dof > 1 else sp.csr_matrix((Ko.reshape(-1), ci, rp), shape=(n, n))).tocsc()
+        xs = spla.spsolve(M, Fo.reshape(-1))
+        xr = np.random.default_rng(4).standard_normal(n)
+        r0, r1 = int(rs[rank]) * dof, int(rs[rank + 1]) * dof
+        g = case.product(rank=rank, size=world, nccl=comm.value, device=local)
+        g.SetForm("SYSTEM", form, [prm[1], prm[0]] if form == "ELASTICITY" else prm)
+        A, B, X, Y = g.CreateMat(), g.CreateVec(), g.CreateVec(), g.CreateVec()
+        g.ComputeSystem(A, B)
+        X.set(xr[r0:r1])
+        g.MatMult(A, X, Y)
+        e_mv = np.linalg.norm(Y.get() - (M @ xr)[r0:r1]) / np.linalg.norm(M @ xr)
+        its, rel = g.Solve(A, B, X, rtol=1e-12, maxits=3000)
+        e_x = np.linalg.norm(X.get() - xs[r0:r1]) / np.linalg.norm(xs)
+        ok = e_mv <= 1e-12 and e_x <= 1e-8 and rel <= 1e-12
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print("%-20s solve      %s matmult=%.1e x=%.1e its=%d rel=%.1e" % (name, "ok " if flag.item() == 0 else "FAIL", e_mv, e_x, its, rel), flush=True)
+        nfail += int(flag.item() != 0)
+        for v in (A, B, X, Y):
+            v.destroy()
+        g.Destroy()
     dist.barrier()
     if rank == 0:
         print("MULTIRANK %s: %d failures on %d ranks" % ("PASS" if nfail == 0 else "FAIL", nfail, world), flush=True)
