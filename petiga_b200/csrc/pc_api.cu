@@ -1,7 +1,11 @@
 // pc_api.cu -- extern "C" entry points of libpetiga_cuda (see include/petiga_cuda.h).
 #include <dlfcn.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -849,7 +853,41 @@ int petiga_cuda_free(void* ptr) { PC_CUDA(cudaFree(ptr)); return 0; }
 int petiga_cuda_memcpy_h2d(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
 int petiga_cuda_memcpy_d2h(void* dst, const void* src, size_t bytes) { PC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
 int petiga_cuda_memset(void* dst, int value, size_t bytes) { PC_CUDA(cudaMemset(dst, value, bytes)); return 0; }
-int petiga_cuda_host_alloc(void** ptr, size_t bytes) { if (!ptr) return PETIGA_CUDA_ERR_ARG; PC_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1)); return 0; }
+// Pinned host memory on the NUMA node of the current device: the pages are placed by first touch, so the calling thread is moved onto
+// the GPU's local CPUs (sysfs local_cpulist of its PCI function) for the allocation and the first touch, then moved back.  With eight
+// ranks copying results out at once, buffers that all sit on one socket share one memory controller and one inter-socket link
+// (round 1: 10.9 GB/s per GPU at N = 8 against 56.6 GB/s at N = 1).  No sysfs entry (containers, single-socket hosts): plain allocation.
+int petiga_cuda_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return PETIGA_CUDA_ERR_ARG;
+  cpu_set_t old_mask, new_mask;
+  bool moved = false;
+  int dev = 0;
+  char bus[32] = {0};
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) == cudaSuccess && sched_getaffinity(0, sizeof(old_mask), &old_mask) == 0) {
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    if (FILE* f = fopen(path.c_str(), "r")) {
+      char line[4096] = {0};
+      if (fgets(line, sizeof(line), f)) {
+        CPU_ZERO(&new_mask);
+        int ncpu = 0;
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+          int a = 0, b = 0;
+          const int k = sscanf(tok, "%d-%d", &a, &b);
+          if (k == 1) b = a;
+          if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &old_mask)) { CPU_SET(c, &new_mask); ncpu++; }
+        }
+        if (ncpu > 0 && sched_setaffinity(0, sizeof(new_mask), &new_mask) == 0) moved = true;
+      }
+      fclose(f);
+    }
+  } else (void)cudaGetLastError();
+  const cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+  if (e == cudaSuccess && bytes) memset(*ptr, 0, bytes);       // first touch while the thread sits next to the device
+  if (moved) sched_setaffinity(0, sizeof(old_mask), &old_mask);
+  PC_CUDA(e);
+  return 0;
+}
 int petiga_cuda_host_free(void* ptr) { PC_CUDA(cudaFreeHost(ptr)); return 0; }
 
 int petiga_cuda_plan_exchange_info(petiga_cuda_plan* P, int kind, int* count, int* out, int capacity) {

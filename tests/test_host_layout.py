@@ -264,3 +264,15 @@ def test_handles_survive_ctypes_above_4gb():
     m = Mat.__new__(Mat)
     m.h = _vp(big)
     assert m.h.value == big
+
+
+def test_glue_compiles():
+    """the replacement bodies of the reference's drivers (integration/petiga_cuda_glue.c, written against the
+    reference's <petiga.h>) are valid C against the C-ABI header; PETSc/PetIGA are absent, so a stub header stands in for them."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(root, "integration", "stub"),
+                        "-I" + os.path.join(root, "include"), os.path.join(root, "integration", "petiga_cuda_glue.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
