@@ -394,7 +394,7 @@ def main():
     roof["frac"] = roof["achieved"] / roof["peak"]
     try:    # dram bytes per launch from the committed ncu --set full capture of the same kernel (profiles/)
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "kron_rows_kernel" if path_used == 2 else "quad_sf_kernel"
+        key = "kron_rows_kernel" if path_used == 2 else quad_kernel_label.split(" ")[0]
         if world == 1 and args.mesh == prof[key]["mesh"] and args.geometry == "identity":
             roof["traffic"] = prof[key]["dram_bytes_per_launch"]
             roof["traffic_source"] = prof[key]["source"]
