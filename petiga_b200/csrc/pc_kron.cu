@@ -58,6 +58,7 @@ struct KronParams {
   unsigned char combo_rs0[36], combo_ij[36], combo_first[37];
   signed char slotA[9], slotB[9];   // ... as (at most) two order-pair indices per block entry, -1 = none; two_slot = 0 when an entry has more
   int two_slot;
+  int bulk;               // dof 1 fast passes: rows staged in shared memory and written by cp.async.bulk (TMA) stores
   KronTerm terms[kMaxTerms];
   KronVTerm vterms[8];
   FixSide bc[3][2];
@@ -715,6 +716,42 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
       grab = __shfl_sync(0xffffffffu, grab, 0);
       const int il = fast_lo + grab * R;
       if (il >= kp.fast_hi) break;
+      if (kp.bulk) {
+        // the R rows of this pass are one contiguous run of R*RW doubles: build it in shared memory and let the TMA engine write it
+        // (cp.async.bulk shared -> global, SASS UBLKCP) instead of 13 x R partial-width (28 of 32 lanes, 224-byte) warp stores.
+        // Source, destination and size must be 16-byte aligned: the run is staged with the parity of its global start, the odd
+        // first / last element goes out with a plain store.
+        double* sb = dynstage + warp * (R * RW + 4);
+        const int64_t gstart = base_lo + (int64_t)(il - fast_lo) * RW;
+        const int par = (int)(gstart & 1);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the previous run of this warp has left the buffer
+        __syncwarp();
+        if (grpF < NGRP) {
+          double a0[R], a3[R];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            a0[r] = __ldg(M0 + (size_t)(ls0 + il + r) * kMaxW + ciF);
+            a3[r] = __ldg(M0 + ((size_t)3 * nnp0 + ls0 + il + r) * kMaxW + ciF);
+          }
+          double* __restrict__ rowp = sb + par + offF;
+#pragma unroll
+          for (int k = 0; k < NITER; k++)
+            if ((k + 1) * NGRP <= WJKC || grpF + k * NGRP < WJKC) {
+              const double x0 = g0[k * NGRP], x3 = g3[k * NGRP];
+#pragma unroll
+              for (int r = 0; r < R; r++) rowp[r * RW + k * OSTEP] = fma(a3[r], x3, a0[r] * x0);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t nbytes = (uint32_t)(R * RW - 2 * par) * 8u;            // R*RW is even: both parities leave a multiple of 16 bytes
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(__cvta_generic_to_global(values + gstart + par)), "r"((uint32_t)__cvta_generic_to_shared(sb + 2 * par)), "r"(nbytes) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (par) { values[gstart] = sb[1]; values[gstart + R * RW - 1] = sb[R * RW]; }
+        }
+      } else
       if (grpF < NGRP) {
         double a0[R], a3[R];
 #pragma unroll
@@ -746,6 +783,7 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
         rhs[lr0 + il + lane] = F;
       }
     }
+    if (kp.bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // all bulk stores of this thread have completed
   }
 }
 
@@ -796,7 +834,8 @@ static int launch_kron_kernel(petiga_cuda_plan* P, const KronParams& kp) {
   int pf = L.ax[0].p;
   for (int d = 1; d < L.dim; d++) if (L.ax[d].p != pf) pf = 0;
   if (L.dim < 3 || (L.dof != 1 && pf > 2)) pf = 0;
-  const size_t dyn = L.dof > 1 ? (size_t)(threads / 32) * kStageCap * sizeof(double) : 0;
+  size_t dyn = L.dof > 1 ? (size_t)(threads / 32) * kStageCap * sizeof(double) : 0;
+  if (L.dof == 1 && kp.bulk && pf > 0) dyn = (size_t)(threads / 32) * (4 * (2 * pf + 1) * (2 * pf + 1) * (2 * pf + 1) + 4) * sizeof(double);
 #define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) { \
     if (dyn) PC_CUDA(cudaFuncSetAttribute(kron_rows_kernel<DOF_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
     kron_rows_kernel<DOF_, PF_><<<blocks, threads, dyn, P->stream>>>(kp); }
@@ -870,6 +909,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
   }
   kp.rowbase = P->d_rowbase; kp.localrow = P->d_localrow; kp.fixtable = P->d_fixtable;
   kp.dim = L.dim; kp.dof = L.dof; kp.block = block; kp.slot = slot; kp.simple = simple; kp.wfull0 = 2 * L.ax[0].p + 1;
+  kp.bulk = P->kron_bulk;
   kp.values = values; kp.rhs = rhs;
   const double* prm = P->slots[slot].prm;
 #define HT(DIM_, DOF_) if (L.dim == DIM_ && L.dof == DOF_) host_terms<DIM_, DOF_>(form, slot, prm, fi, kp);
