@@ -237,21 +237,37 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < k3MaxPairs) ccS[tid] = sp.cconst[tid];
-  if (tid < k3AsmThreads && (tid & 31) == 0) {          // the warp's stage A + B program (see sf3r_stage_ab)
-    uint32_t* pg = progS + (tid >> 5) * k3rMaxOps;
-    int n = 0;
-    for (int combo = tid >> 5; combo < ls.ng2 * 4; combo += 8) {
-      const int g2 = combo >> 2, q2 = combo & 3;
+  if (tid == 0) {   // the warps' stage A + B programs (see sf3r_stage_ab): combinations dealt out longest first to the least loaded warp
+    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ncmb = ls.ng2 * 4;
+    bool done[16];
+    for (int k = 0; k < 16; k++) done[k] = false;
+    for (int k = 0; k < ncmb; k++) {
+      int best = -1, bestn = -1;
+      for (int cmb = 0; cmb < ncmb; cmb++) {
+        if (done[cmb]) continue;
+        const int g2 = cmb >> 2;
+        const int nop = ls.g1_first[ls.g2_first[g2 + 1]] - ls.g1_first[ls.g2_first[g2]];
+        if (nop > bestn) { bestn = nop; best = cmb; }
+      }
+      done[best] = true;
+      int wmin = 0;
+      for (int w = 1; w < 8; w++) if (load[w] < load[wmin]) wmin = w;
+      uint32_t* pg = progS + wmin * k3rMaxOps;
+      int n = load[wmin];
+      const int g2 = best >> 2, q2 = best & 3;
       bool firstc = true;
       for (int g1 = ls.g2_first[g2]; g1 < ls.g2_first[g2 + 1]; g1++)
         for (int pr = ls.g1_first[g1]; pr < ls.g1_first[g1 + 1]; pr++) {
           const bool f1 = pr == ls.g1_first[g1], l1 = pr + 1 == ls.g1_first[g1 + 1], lc = l1 && g1 + 1 == ls.g2_first[g2 + 1];
-          pg[n++] = (uint32_t)ls.pair_oo0[pr] | ((uint32_t)pr << 4) | ((uint32_t)ls.g1_oo1[g1] << 8) | ((uint32_t)q2 << 12) | ((uint32_t)g2 << 14) |
-                    ((uint32_t)f1 << 16) | ((uint32_t)l1 << 17) | ((uint32_t)firstc << 18) | ((uint32_t)lc << 19);
+          if (n < k3rMaxOps - 1)
+            pg[n++] = (uint32_t)ls.pair_oo0[pr] | ((uint32_t)pr << 4) | ((uint32_t)ls.g1_oo1[g1] << 8) | ((uint32_t)q2 << 12) | ((uint32_t)g2 << 14) |
+                      ((uint32_t)f1 << 16) | ((uint32_t)l1 << 17) | ((uint32_t)firstc << 18) | ((uint32_t)lc << 19);
           firstc = false;
         }
+      load[wmin] = n;
     }
-    pg[k3rMaxOps - 1] = (uint32_t)n;
+    for (int w = 0; w < 8; w++) progS[w * k3rMaxOps + k3rMaxOps - 1] = (uint32_t)load[w];
   }
   __syncthreads();
 
