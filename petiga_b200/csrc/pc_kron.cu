@@ -29,7 +29,7 @@ namespace {
 constexpr int kMaxTerms = 40;
 constexpr int kKronP = 4;               // the separable path keeps its pencil tables in static shared memory: degree <= 4
 constexpr int kMaxWW = (2 * kKronP + 1) * (2 * kKronP + 1);
-constexpr int kStageCap = 1218;         // dof > 1: doubles of dynamic shared memory per warp (one p = 2 BAIJ row of 125 3x3 blocks + its coefficients)
+constexpr int kStageCap = 32 * 16 + 192;         // dof > 1: doubles of dynamic shared memory per warp (one p = 2 BAIJ row of 125 3x3 blocks + its coefficients)
 
 struct KronTerm { unsigned char ij, rs0, rs1, rs2; double c; };
 struct KronVTerm { unsigned char i, r0, r1, r2; double c; };
@@ -270,44 +270,21 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
       nfast = kp.fast_hi - fast_lo;
     }
   }
-  // ---- dof > 1: a lane owns one (j,k) column offset of the pencil and keeps its G values in REGISTERS for all rows of the pencil
-  //      (G does not depend on the axis-0 row); a row is built in shared memory in storage order and written with full-width
-  //      warp stores.  Was: 18 shared-memory loads per block in every row + a 288-double staging round trip per 30 blocks
-  //      (cfg 4: 2.63 ms = 47 % of the HBM rate). ----
+  // ---- dof > 1, interior stretch of a pencil (the same row range as the scalar fast passes): see the register-direct passes after
+  //      the general loop ----
   constexpr int DD = DOF * DOF;
   bool blk_fast = false;
-  double gA[DD], gB[DD];
   if constexpr (DOF > 1 && PF > 0) {
     constexpr int WIC = 2 * PF + 1;
     const bool row_jk_bc = fixing && ((rcj && (kp.bc[1][rcj - 1].vcount || kp.bc[1][rcj - 1].lcount)) || (rck && (kp.bc[2][rck - 1].vcount || kp.bc[2][rck - 1].lcount)));
     blk_fast = want_mat && kp.two_slot && kp.dim == 3 && simple_jk && !jk_boundary && !row_jk_bc && Wjk == WIC * WIC && WiF == WIC &&
-               WIC * WIC <= 32 && ((WIC * WIC * WIC * DD + 2) & ~1) + WIC * DD * 2 <= kStageCap;
-    if (blk_fast) {
-#pragma unroll
-      for (int ij = 0; ij < DD; ij++) {
-        gA[ij] = (lane < Wjk && kp.slotA[ij] >= 0) ? G[kp.slotA[ij]][ij][lane] : 0.0;
-        gB[ij] = (lane < Wjk && kp.slotB[ij] >= 0) ? G[kp.slotB[ij]][ij][lane] : 0.0;
-      }
-    }
+               kp.fast_hi > fast_lo && (nwarps & 1) == 0;
+    if (blk_fast) nfast = kp.fast_hi - fast_lo;
   }
   const int nslow = lw0 - nfast;   // the general loop walks the remaining rows (compacted index)
   // per-row parameters are prefetched one row ahead (registers), so that their L2 latency overlaps the stores of the
   // current row instead of stalling every row (ncu r1_ncu_kron_rows_mesh128_v3: long_scoreboard was the top stall)
-  constexpr int NAC = (DOF > 1 && PF > 0) ? ((2 * PF + 1) * DD * 2 + 31) / 32 : 1;   // dof > 1 fast path: this lane's axis-0 factors of a row
-  int acoff[NAC];
-#pragma unroll
-  for (int k = 0; k < NAC; k++) {
-    acoff[k] = -1;
-    if (DOF > 1 && PF > 0) {
-      const int t = lane + 32 * k;
-      if (t < (2 * PF + 1) * DD * 2) {
-        const int ci = t / (DD * 2), r2 = t - ci * (DD * 2), ij = r2 >> 1;
-        const int rs = (r2 & 1) ? kp.slotB[ij] : kp.slotA[ij];
-        if (rs >= 0) acoff[k] = rs * nnp0 * kMaxW + ci;
-      }
-    }
-  }
-  struct RowP { int Wi, fi, simple; int64_t base; double a0, a3; double acv[NAC]; };
+  struct RowP { int Wi, fi, simple; int64_t base; double a0, a3; };
   auto load_row = [&](int il_) {
     RowP r;
     const int Ai_ = ls0 + il_, gi_ = Ai_ - gs0;
@@ -315,8 +292,6 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
     r.base = __ldg(rowbase + il_ + lr0);
     r.a0 = r.a3 = 0.0;
     if (DOF == 1) { r.a0 = __ldg(M0 + (size_t)Ai_ * kMaxW + ciF); r.a3 = __ldg(M0 + ((size_t)3 * nnp0 + Ai_) * kMaxW + ciF); }   // only the scalar fast paths use them
-#pragma unroll
-    for (int k = 0; k < NAC; k++) r.acv[k] = (DOF > 1 && PF > 0 && blk_fast && acoff[k] >= 0) ? __ldg(M0 + acoff[k] + (size_t)Ai_ * kMaxW) : 0.0;
     return r;
   };
   RowP cur, nxt;
@@ -332,74 +307,6 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
     const int lr = il + lr0;
     const int64_t base = cur.base;
     const bool SIMPLE = simple_jk && cur.simple;
-    if constexpr (DOF > 1 && PF > 0) {
-      if (blk_fast && SIMPLE && Wi == WiF && !(fixing && !per0 && (Ai == 0 || Ai == nnp0 - 1 || fi == 0 || fi + Wi == nnp0))) {
-        constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, WR = WIC * WJKC, NV = WR * DD;       // all extents static: fully unrolled
-        double* stg0 = dynstage + warp * kStageCap;
-        double* ac = stg0 + ((NV + 2) & ~1);                           // ac[ci][ij][2]: the row's axis-0 factors of the two order pairs
-        const int al = (int)((base * DD) & 1);                         // stage with the parity of the destination: 16-byte stores line up
-        double* stg = stg0 + al;
-#pragma unroll
-        for (int k = 0; k < NAC; k++) {
-          const int t = lane + 32 * k;
-          if (t < WIC * DD * 2) ac[t] = cur.acv[k];                   // loaded one row ahead with the row parameters
-        }
-        __syncwarp();
-        if (lane < WJKC) {
-          if (kp.block) {
-#pragma unroll
-            for (int ci = 0; ci < WIC; ci++) {
-              double* o = stg + (lane * WIC + ci) * DD;
-#pragma unroll
-              for (int ij = 0; ij < DD; ij++) {
-                const double2 a2 = *reinterpret_cast<const double2*>(ac + (ci * DD + ij) * 2);
-                o[(ij % DOF) * DOF + ij / DOF] = fma(a2.y, gB[ij], a2.x * gA[ij]);      // column-major block
-              }
-            }
-          } else {
-#pragma unroll
-            for (int ci = 0; ci < WIC; ci++) {
-              double* o = stg + (lane * WIC + ci) * DOF;
-#pragma unroll
-              for (int ij = 0; ij < DD; ij++) {
-                const double2 a2 = *reinterpret_cast<const double2*>(ac + (ci * DD + ij) * 2);
-                o[(ij / DOF) * WR * DOF + ij % DOF] = fma(a2.y, gB[ij], a2.x * gA[ij]);
-              }
-            }
-          }
-        }
-        __syncwarp();
-        double* __restrict__ dst = values + (size_t)base * DD;
-        if (al && lane == 0) dst[0] = stg[0];                          // head element of an odd row start
-        {
-          const double2* __restrict__ s2 = reinterpret_cast<const double2*>(stg + al);
-          double2* __restrict__ d2 = reinterpret_cast<double2*>(dst + al);
-          constexpr int NP = (NV - 1) / 2;                             // pairs that exist for either parity
-#pragma unroll
-          for (int k = 0; k < (NP + 31) / 32; k++) {
-            const int t = lane + 32 * k;
-            if (t < NP) d2[t] = s2[t];
-          }
-          // tail: NV - al - 2 NP elements (0, 1 or 2) after the pairs
-          const int done = al + 2 * NP;
-          if (lane < NV - done) dst[done + lane] = stg[done + lane];
-        }
-        __syncwarp();
-        if (want_vec && lane == 0) {
-#pragma unroll
-          for (int cc = 0; cc < DOF; cc++) {
-            double F = 0.0;
-            for (int n = 0; n < kp.nvterms; n++) {
-              const KronVTerm vt = kp.vterms[n];
-              if (vt.i != cc) continue;
-              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
-            }
-            rhs[(size_t)lr * DOF + cc] = F;
-          }
-        }
-        continue;
-      }
-    }
     if (fast_ok) {
       const bool rowb = fixing && ((!per0 && (Ai == 0 || Ai == nnp0 - 1)) || rcj || rck);
       const bool colb = jk_boundary || (fixing && !per0 && (fi == 0 || fi + Wi == nnp0));
@@ -698,6 +605,82 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
           F += racc[c];
           if (rfix[c]) F = nelem * rval[c];
           kp.rhs[(size_t)lr * DOF + c] = F;
+        }
+      }
+    }
+  }
+  // ---- dof > 1: register-direct rows.  A row of the interior stretch is WR blocks of DD doubles, contiguous in memory.  A lane owns
+  //      the output positions t = 32 k + lane of HALF a row (two warps per row); the G factors of its positions do not depend on
+  //      the axis-0 row, so they live in registers for the whole pencil (2 x KH doubles); per row only the 2 x WIC x DD axis-0 factors
+  //      are staged (90 doubles at p = 2, loaded one row ahead), and every store instruction writes 256 contiguous bytes.
+  //      Was (ncu r2_ncu_kron_cfg4_v2): the row built in shared memory and copied out -- 302 LSU wavefronts per 9 000-byte row
+  //      against 220 cycles at HBM rate. ----
+  if constexpr (DOF > 1 && PF > 0) {
+    if (blk_fast) {
+      constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, WR = WIC * WJKC, NV = WR * DD, KT = (NV + 31) / 32, KH = (KT + 1) / 2;
+      constexpr int NACV = (WIC * DD * 2 + 31) / 32;
+      const int h = warp & 1, pairi = warp >> 1, npair = nwarps >> 1;
+      double gA[KH], gB[KH];
+      int aoff[KH];
+#pragma unroll
+      for (int k = 0; k < KH; k++) {
+        const int t = 32 * (h * KH + k) + lane;
+        gA[k] = gB[k] = 0.0; aoff[k] = 0;
+        if (t < NV) {
+          int blk, i, j;
+          if (kp.block) { blk = t / DD; const int e = t - blk * DD; j = e / DOF; i = e - j * DOF; }          // column-major blocks
+          else { i = t / (WR * DOF); const int r2 = t - i * (WR * DOF); blk = r2 / DOF; j = r2 - blk * DOF; }   // DOF scalar rows
+          const int ij = i * DOF + j, cjk = blk / WIC, ci = blk - cjk * WIC;
+          if (kp.slotA[ij] >= 0) gA[k] = G[kp.slotA[ij]][ij][cjk];
+          if (kp.slotB[ij] >= 0) gB[k] = G[kp.slotB[ij]][ij][cjk];
+          aoff[k] = (ci * DD + ij) * 2;
+        }
+      }
+      int acg[NACV];                                             // this lane's entries of the staged table ac[ci][ij][2] -> offsets into M0
+#pragma unroll
+      for (int k = 0; k < NACV; k++) {
+        acg[k] = -1;
+        const int t = lane + 32 * k;
+        if (t < WIC * DD * 2) {
+          const int ci = t / (DD * 2), r2 = t - ci * (DD * 2), ij = r2 >> 1;
+          const int rs = (r2 & 1) ? kp.slotB[ij] : kp.slotA[ij];
+          if (rs >= 0) acg[k] = rs * nnp0 * kMaxW + ci;
+        }
+      }
+      double* acs = dynstage + warp * kStageCap + 32 * DD;       // (the general path's staging area comes first)
+      double acv[NACV];
+      int il = fast_lo + pairi;
+#pragma unroll
+      for (int k = 0; k < NACV; k++) acv[k] = (il < kp.fast_hi && acg[k] >= 0) ? __ldg(M0 + acg[k] + (size_t)(ls0 + il) * kMaxW) : 0.0;
+      for (; il < kp.fast_hi; il += npair) {
+        const int Ai = ls0 + il, lr = il + lr0;
+        const int64_t base = __ldg(rowbase + lr);
+#pragma unroll
+        for (int k = 0; k < NACV; k++) { const int t = lane + 32 * k; if (t < WIC * DD * 2) acs[t] = acv[k]; }
+        const int iln = il + npair;
+#pragma unroll
+        for (int k = 0; k < NACV; k++) acv[k] = (iln < kp.fast_hi && acg[k] >= 0) ? __ldg(M0 + acg[k] + (size_t)(ls0 + iln) * kMaxW) : 0.0;
+        __syncwarp();
+        double* __restrict__ dst = values + (size_t)base * DD + 32 * (h * KH) + lane;
+#pragma unroll
+        for (int k = 0; k < KH; k++) {
+          if (32 * (h * KH + k) + 31 < NV || 32 * (h * KH + k) + lane < NV) {
+            const double2 a2 = *reinterpret_cast<const double2*>(acs + aoff[k]);
+            dst[32 * k] = fma(a2.y, gB[k], a2.x * gA[k]);
+          }
+        }
+        __syncwarp();
+        if (want_vec && h == 0 && lane == 0) {
+#pragma unroll
+          for (int cc = 0; cc < DOF; cc++) {
+            double F = 0.0;
+            for (int n = 0; n < kp.nvterms; n++) {
+              const KronVTerm vt = kp.vterms[n];
+              if (vt.i != cc) continue;
+              F += vt.c * kp.mv[0][vt.r0 * nnp0 + Ai] * kp.mv[1][vt.r1 * kp.nnp[1] + Aj] * kp.mv[2][vt.r2 * kp.nnp[2] + Ak];
+            }
+            rhs[(size_t)lr * DOF + cc] = F;
+          }
         }
       }
     }
