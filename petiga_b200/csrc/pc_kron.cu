@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
   if constexpr (DOF > 1 && PF > 0) {
     constexpr int WIC = 2 * PF + 1;
     const bool row_jk_bc = fixing && ((rcj && (kp.bc[1][rcj - 1].vcount || kp.bc[1][rcj - 1].lcount)) || (rck && (kp.bc[2][rck - 1].vcount || kp.bc[2][rck - 1].lcount)));
-    blk_fast = want_mat && kp.two_slot && kp.dim == 3 && simple_jk && !jk_boundary && !row_jk_bc && Wjk == WIC * WIC && WiF == WIC &&
-               kp.fast_hi > fast_lo && (nwarps & 1) == 0;
+    blk_fast = want_mat && kp.two_slot && kp.dim == 3 && simple_jk && !jk_boundary && !row_jk_bc && Wjk <= WIC * WIC && WiF == WIC &&
+               kp.fast_hi > fast_lo && (nwarps & 1) == 0;           // (pencils next to a j/k end have fewer columns: same code, shorter rows)
     if (blk_fast) nfast = kp.fast_hi - fast_lo;
   }
   const int nslow = lw0 - nfast;   // the general loop walks the remaining rows (compacted index)
@@ -617,9 +617,11 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
   //      against 220 cycles at HBM rate. ----
   if constexpr (DOF > 1 && PF > 0) {
     if (blk_fast) {
-      constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, WR = WIC * WJKC, NV = WR * DD, KT = (NV + 31) / 32, KH = (KT + 1) / 2;
+      constexpr int NSPLIT = 2;                                   // warps per row (measured: 4 warps per row at 3 CTAs per SM spills and is 10 % slower)
+      constexpr int WIC = 2 * PF + 1, WJKC = WIC * WIC, KT = (WIC * WJKC * DD + 31) / 32, KH = (KT + NSPLIT - 1) / NSPLIT;
       constexpr int NACV = (WIC * DD * 2 + 31) / 32;
-      const int h = warp & 1, pairi = warp >> 1, npair = nwarps >> 1;
+      const int WR = WIC * Wjk, NV = WR * DD;                     // blocks / doubles of a full-width row of THIS pencil
+      const int h = warp % NSPLIT, pairi = warp / NSPLIT, npair = nwarps / NSPLIT;
       double gA[KH], gB[KH];
       int aoff[KH];
 #pragma unroll
@@ -633,7 +635,9 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
           const int ij = i * DOF + j, cjk = blk / WIC, ci = blk - cjk * WIC;
           if (kp.slotA[ij] >= 0) gA[k] = G[kp.slotA[ij]][ij][cjk];
           if (kp.slotB[ij] >= 0) gB[k] = G[kp.slotB[ij]][ij][cjk];
-          aoff[k] = (ci * DD + ij) * 2;
+          // the staged table is ordered like the outputs (BAIJ: q = position inside the column-major block), so that consecutive
+          // lanes read consecutive 16-byte entries: no bank conflicts
+          aoff[k] = (ci * DD + (kp.block ? j * DOF + i : ij)) * 2;
         }
       }
       int acg[NACV];                                             // this lane's entries of the staged table ac[ci][ij][2] -> offsets into M0
@@ -642,7 +646,8 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
         acg[k] = -1;
         const int t = lane + 32 * k;
         if (t < WIC * DD * 2) {
-          const int ci = t / (DD * 2), r2 = t - ci * (DD * 2), ij = r2 >> 1;
+          const int ci = t / (DD * 2), r2 = t - ci * (DD * 2), q = r2 >> 1;
+          const int ij = kp.block ? (q % DOF) * DOF + q / DOF : q;
           const int rs = (r2 & 1) ? kp.slotB[ij] : kp.slotA[ij];
           if (rs >= 0) acg[k] = rs * nnp0 * kMaxW + ci;
         }
@@ -652,9 +657,11 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
       int il = fast_lo + pairi;
 #pragma unroll
       for (int k = 0; k < NACV; k++) acv[k] = (il < kp.fast_hi && acg[k] >= 0) ? __ldg(M0 + acg[k] + (size_t)(ls0 + il) * kMaxW) : 0.0;
+      int64_t base_n = il < kp.fast_hi ? __ldg(rowbase + lr0 + il) : 0;
       for (; il < kp.fast_hi; il += npair) {
         const int Ai = ls0 + il, lr = il + lr0;
-        const int64_t base = __ldg(rowbase + lr);
+        const int64_t base = base_n;                             // (row parameters are loaded one row ahead)
+        if (il + npair < kp.fast_hi) base_n = __ldg(rowbase + lr + npair);
 #pragma unroll
         for (int k = 0; k < NACV; k++) { const int t = lane + 32 * k; if (t < WIC * DD * 2) acs[t] = acv[k]; }
         const int iln = il + npair;
@@ -662,11 +669,16 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
         for (int k = 0; k < NACV; k++) acv[k] = (iln < kp.fast_hi && acg[k] >= 0) ? __ldg(M0 + acg[k] + (size_t)(ls0 + iln) * kMaxW) : 0.0;
         __syncwarp();
         double* __restrict__ dst = values + (size_t)base * DD + 32 * (h * KH) + lane;
+        constexpr int KB = (KH + 2) / 3;                        // three batches: all loads of a batch issue before its stores
 #pragma unroll
-        for (int k = 0; k < KH; k++) {
-          if (32 * (h * KH + k) + 31 < NV || 32 * (h * KH + k) + lane < NV) {
-            const double2 a2 = *reinterpret_cast<const double2*>(acs + aoff[k]);
-            dst[32 * k] = fma(a2.y, gB[k], a2.x * gA[k]);
+        for (int b3 = 0; b3 < 3; b3++) {
+          double2 a2[KB];
+#pragma unroll
+          for (int kk = 0; kk < KB; kk++) { const int k = b3 * KB + kk; if (k < KH) a2[kk] = *reinterpret_cast<const double2*>(acs + aoff[k]); }
+#pragma unroll
+          for (int kk = 0; kk < KB; kk++) {
+            const int k = b3 * KB + kk;
+            if (k < KH && 32 * (h * KH + k) + lane < NV) dst[32 * k] = fma(a2[kk].y, gB[k], a2[kk].x * gA[k]);
           }
         }
         __syncwarp();
