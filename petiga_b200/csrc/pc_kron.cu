@@ -174,9 +174,14 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
   // a pencil's prologue used to be 25-49 threads walking all terms with two dependent global loads each (27 terms for
   // elasticity: ~10 000 cycles per CTA, two thirds of a cfg-4 CTA's life)
   __shared__ double sM[2][4][kMaxW];
+  __shared__ uint32_t sSeg[2][kMaxW];            // packed (B, S, L) bytes of this pencil's axis-1 / axis-2 rows
   for (int t = threadIdx.x; t < 2 * 4 * kMaxW; t += blockDim.x) {
     const int d = t / (4 * kMaxW), rs = (t / kMaxW) & 3, cc = t % kMaxW;
     (&sM[0][0][0])[t] = kp.M[1 + d][((size_t)rs * kp.nnp[1 + d] + (d ? Ak : Aj)) * kMaxW + cc];
+  }
+  if (threadIdx.x < 2 * kMaxW) {
+    const int d = threadIdx.x / kMaxW, cc = threadIdx.x % kMaxW;
+    sSeg[d][cc] = kp.seg[1 + d][(d ? gk : gj) * kMaxW + cc];
   }
   for (int t = threadIdx.x; t < 4 * DOF * DOF * kMaxWW; t += blockDim.x) (&G[0][0][0])[t] = 0.0;
   if (threadIdx.x == 0) fast_ctr = 0;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(cons
     if (cj == Aj - fj && ck == Ak - fk) info |= 16;
     int p1 = 0;
     {
-      const uint32_t s1 = kp.seg[1][gj * kMaxW + cj], s2 = kp.seg[2][gk * kMaxW + ck];
+      const uint32_t s1 = sSeg[0][cj], s2 = sSeg[1][ck];
       const int Bj = s1 & 255, Sj = (s1 >> 8) & 255, Lj = (s1 >> 16) & 255;
       const int Bk = s2 & 255, Sk = (s2 >> 8) & 255, Lk = (s2 >> 16) & 255;
       p1 = Bk * Wj + Sk * Bj;
