@@ -41,9 +41,11 @@ int launch_quadrature_vec3(petiga_cuda_plan* Pl, const KParams& base) {
   sp.want_vec = 1;
   if (base.nelem <= 0) return 0;
   const int n3 = (p + 1) * (p + 1) * (p + 1), threads = (n3 + 31) / 32 * 32;
-  if (p == 2) quad_vec3_kernel<2><<<base.nelem, threads, 0, Pl->stream>>>(sp);
-  else if (p == 3) quad_vec3_kernel<3><<<base.nelem, threads, 0, Pl->stream>>>(sp);
-  else quad_vec3_kernel<4><<<base.nelem, threads, 0, Pl->stream>>>(sp);
+  if (base.ax[1].ew > 65535 || base.ax[2].ew > 65535) return nope("element box too large for a 3-D grid");
+  const dim3 grid3((unsigned)base.ax[0].ew, (unsigned)base.ax[1].ew, (unsigned)base.ax[2].ew);
+#define VK(P_) { if (base.X) quad_vec3_kernel<P_, true><<<grid3, threads, 0, Pl->stream>>>(sp); else quad_vec3_kernel<P_, false><<<grid3, threads, 0, Pl->stream>>>(sp); }
+  if (p == 2) VK(2) else if (p == 3) VK(3) else VK(4)
+#undef VK
   PC_CUDA(cudaGetLastError());
   Pl->launches++;
   const double n4 = (double)(p + 1) * (p + 1) * (p + 1) * (p + 1);
@@ -131,7 +133,17 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
     }
     sp.dprime = Pl->d_sf3_dprime;
   }
-  if ((mapped && sp.want_mat) || sp.want_vec) {
+  if (mapped && sp.want_mat) {          // geometry pre-pass: D' for the matrix kernel (+ the element vectors on the way)
+    sf3_geom_kernel<<<base.nelem, 64, 0, Pl->stream>>>(sp);
+    PC_CUDA(cudaGetLastError());
+    Pl->launches++;
+  } else if (sp.want_vec && NV > 0 && base.ax[1].ew <= 65535 && base.ax[2].ew <= 65535) {   // vector only: the lean vector kernel (pc_quadv.cuh)
+    const dim3 grid3((unsigned)base.ax[0].ew, (unsigned)base.ax[1].ew, (unsigned)base.ax[2].ew);
+    if (mapped) quad_vec3_kernel<3, true><<<grid3, 64, 0, Pl->stream>>>(sp);
+    else quad_vec3_kernel<3, false><<<grid3, 64, 0, Pl->stream>>>(sp);
+    PC_CUDA(cudaGetLastError());
+    Pl->launches++;
+  } else if (sp.want_vec) {
     sf3_geom_kernel<<<base.nelem, 64, 0, Pl->stream>>>(sp);
     PC_CUDA(cudaGetLastError());
     Pl->launches++;

@@ -12,21 +12,20 @@
 
 namespace pc {
 
-template <int P>
+// MAPPED is a template parameter so that the identity-geometry instantiation carries no geometry scratch: 13 KB instead of 35 KB of
+// shared memory at p = 4, i.e. 16 instead of 6 resident CTAs per SM for a kernel that is latency bound (table loads, 5 barriers)
+template <int P, bool MAPPED>
 __global__ void __launch_bounds__(((P + 1) * (P + 1) * (P + 1) + 31) / 32 * 32) quad_vec3_kernel(const __grid_constant__ SF3Params sp) {
   constexpr int N = P + 1, NN = N * N, NNN = N * N * N, T = (NNN + 31) / 32 * 32;
   const KParams& prm = sp.k;
   const SFLists& ls = sp.l;
-  __shared__ double gB[3 * 2 * NN], wJ[3 * N], pt[3 * N], Xs[3 * NNN], T1[3 * 2 * N * NN], T2[3 * 3 * NNN], Ev[3 * 4 * NNN], Fp[4 * NNN];
+  __shared__ double gB[3 * 2 * NN], wJ[3 * N], pt[3 * N], Fp[4 * NNN];
+  __shared__ double Xs[MAPPED ? 3 * NNN : 1], Ev[MAPPED ? 3 * 4 * NNN : 1];
+  __shared__ double T1[MAPPED ? 3 * 2 * N * NN : 4 * NNN], T2[MAPPED ? 3 * 3 * NNN : 4 * NNN];   // (also R1 / R2 of the transposed stages)
   const int gt = threadIdx.x;
   const int NV = prm.vc1 - prm.vc0, NT = ls.NT;
-  const bool mapped = prm.X != nullptr;
-  int ID[3];
-  {
-    int idx = blockIdx.x;
-#pragma unroll
-    for (int d = 0; d < 3; d++) { const int cc = idx % prm.ax[d].ew; idx /= prm.ax[d].ew; ID[d] = cc + prm.ax[d].es; }
-  }
+  constexpr bool mapped = MAPPED;
+  const int ID[3] = {(int)blockIdx.x + prm.ax[0].es, (int)blockIdx.y + prm.ax[1].es, (int)blockIdx.z + prm.ax[2].es};   // 3-D grid: no divisions
   for (int t = gt; t < 3 * 2 * NN; t += T) {
     const int d = t / (2 * NN), r = t % (2 * NN), o = r / NN, q = (r / N) % N, a = r % N;
     gB[t] = prm.ax[d].value[((size_t)(ID[d] * N + q) * N + a) * 5 + o];                 // Bt[d][o][q][a]
@@ -110,21 +109,34 @@ __global__ void __launch_bounds__(((P + 1) * (P + 1) * (P + 1) + 31) / 32 * 32) 
       form_coefficients<3, 1>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, 0, NV, nullptr, fv);
     }
     // f'[s][q] = JW sum_al A[vc0 + al][s] f[al],  A[0][tN] = 1, A[1 + i][tG_d] = E[d][i]
+    if (!MAPPED) {   // E = I: component ca feeds exactly one tensor slot
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-      double acc = 0.0;
+      for (int s = 0; s < 4; s++) {
+        double acc = 0.0;
 #pragma unroll
-      for (int al = 0; al < 4; al++) {
-        const int ca = prm.vc0 + al;
-        double as = 0.0;
-        if (ca == 0) as = (s == ls.tN) ? 1.0 : 0.0;
-        else if (ca <= 3) {
-#pragma unroll
-          for (int d = 0; d < 3; d++) if (s == ls.tG[d]) as = E[d][ca - 1];
+        for (int al = 0; al < 4; al++) {
+          const int ca = prm.vc0 + al, ts = (ca == 0) ? ls.tN : (ca <= 3 ? ls.tG[ca - 1] : -1);
+          if (al < NV && ts == s) acc += fv[al];
         }
-        if (al < NV) acc = fma(as, fv[al], acc);
+        if (s < NT) Fp[s * NNN + q] = acc * jw;
       }
-      if (s < NT) Fp[s * NNN + q] = acc * jw;
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int al = 0; al < 4; al++) {
+          const int ca = prm.vc0 + al;
+          double as = 0.0;
+          if (ca == 0) as = (s == ls.tN) ? 1.0 : 0.0;
+          else if (ca <= 3) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) if (s == ls.tG[d]) as = E[d][ca - 1];
+          }
+          if (al < NV) acc = fma(as, fv[al], acc);
+        }
+        if (s < NT) Fp[s * NNN + q] = acc * jw;
+      }
     }
   }
   __syncthreads();
