@@ -360,6 +360,7 @@ int petiga_cuda_set_option(petiga_cuda_plan* P, const char* name, double value) 
   if (!strcmp(name, "scatter")) { P->scatter = (int)value; return 0; }
   if (!strcmp(name, "quad_impl")) { int v = (int)value; if (v < -1 || v > 3) return PETIGA_CUDA_ERR_ARG; P->quad_impl = v; return 0; }
   if (!strcmp(name, "kron_bulk")) { P->kron_bulk = value != 0; P->config_version++; return 0; }
+  if (!strcmp(name, "sf3_static")) { P->sf3_static = value != 0; return 0; }
   if (!strcmp(name, "sf3_variant")) { int v = (int)value; if (v < 0 || v > 1) return PETIGA_CUDA_ERR_ARG; P->sf3_variant = v; return 0; }
   set_error(std::string("unknown option ") + name);
   return PETIGA_CUDA_ERR_ARG;
@@ -370,6 +371,7 @@ int petiga_cuda_get_stat(petiga_cuda_plan* P, const char* name, double* value) {
   if (!strcmp(name, "launches")) { *value = (double)P->launches; return 0; }
   if (!strcmp(name, "last_path")) { *value = (double)P->last_path; return 0; }
   if (!strcmp(name, "last_impl")) { *value = (double)P->last_impl; return 0; }
+  if (!strcmp(name, "last_sf3_static")) { *value = (double)P->last_sf3_static; return 0; }
   if (!strcmp(name, "last_sf3_variant")) { *value = (double)P->last_sf3_variant; return 0; }
   if (!strcmp(name, "last_kernel_ms")) { *value = P->last_kernel_ms; return 0; }
   if (!strcmp(name, "last_flops")) { *value = P->last_flops; return 0; }

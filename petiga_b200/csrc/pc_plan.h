@@ -81,6 +81,7 @@ struct petiga_cuda_plan {
   int kron_bulk = 0;              // separable path, dof 1: 1 = rows staged in shared memory and written by cp.async.bulk stores
   int sf3_variant = 0;            // third-generation kernel: 0 = register-carried rows where the axis-0 rows advance one per element, 1 = shared-memory window always
   int last_sf3_variant = 0;
+  int sf3_static = 1, last_sf3_static = 0;   // 1: use the compiled-in form structure when the run-time lists match it (0: always interpret)
   int quad_impl = -1;             // -1 = choose by element size, 0 = sum-factorised kernel, 1 = pair-loop kernel
   // stats
   long launches = 0;

@@ -1,5 +1,7 @@
 // pc_quad3.cu -- launcher of the third-generation quadrature kernel (pc_quad3.cuh).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -153,9 +155,32 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
     const SF3RSmem layr(sp.l.npairs, mapped ? 1 : 0);
     if (smooth0 && Pl->sf3_variant == 0 && (size_t)layr.total * 8 <= 227 * 1024) {   // rows carried in the DMMA accumulators
       const size_t smem = (size_t)layr.total * 8;
-      PC_CUDA(cudaFuncSetAttribute(quad_sf3r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      quad_sf3r_kernel<<<blocks, k3rThreads, smem, Pl->stream>>>(sp);
+      auto same = [&](const SF3RStruct& S) {      // exact match of the run-time lists with a compiled-in structure
+        if (sp.l.ng2 != S.ng2 || sp.l.ng1 != S.ng1 || sp.l.npairs != S.npairs) return false;
+        for (int k = 0; k <= S.ng2; k++) if (sp.l.g2_first[k] != S.g2_first[k]) return false;
+        for (int k = 0; k < S.ng2; k++) if (sp.l.g2_oo2[k] != S.g2_oo2[k]) return false;
+        for (int k = 0; k <= S.ng1; k++) if (sp.l.g1_first[k] != S.g1_first[k]) return false;
+        for (int k = 0; k < S.ng1; k++) if (sp.l.g1_oo1[k] != S.g1_oo1[k]) return false;
+        for (int k = 0; k < S.npairs; k++) if (sp.l.pair_oo0[k] != S.pair_oo0[k]) return false;
+        return true;
+      };
+      if (getenv("PETIGA_SF3_DUMP")) {
+        printf("sf3 lists: mapped=%d ng2=%d ng1=%d npairs=%d\n g2_first:", (int)mapped, sp.l.ng2, sp.l.ng1, sp.l.npairs);
+        for (int k = 0; k <= sp.l.ng2; k++) printf(" %d", sp.l.g2_first[k]);
+        printf("\n g2_oo2:"); for (int k = 0; k < sp.l.ng2; k++) printf(" %d", sp.l.g2_oo2[k]);
+        printf("\n g1_first:"); for (int k = 0; k <= sp.l.ng1; k++) printf(" %d", sp.l.g1_first[k]);
+        printf("\n g1_oo1:"); for (int k = 0; k < sp.l.ng1; k++) printf(" %d", sp.l.g1_oo1[k]);
+        printf("\n pair_oo0:"); for (int k = 0; k < sp.l.npairs; k++) printf(" %d", sp.l.pair_oo0[k]);
+        printf("\n pair_s/t:"); for (int k = 0; k < sp.l.npairs; k++) printf(" (%d,%d)", sp.l.pair_s[k], sp.l.pair_t[k]);
+        printf("\n"); fflush(stdout);
+      }
+      const int fs = Pl->sf3_static == 0 ? 0 : (!mapped && same(k3rStructDiag)) ? 1 : (mapped && same(k3rStructFull)) ? 2 : 0;
+#define SF3R_LAUNCH(FS_) { PC_CUDA(cudaFuncSetAttribute(quad_sf3r_kernel<FS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                           quad_sf3r_kernel<FS_><<<blocks, k3rThreads, smem, Pl->stream>>>(sp); }
+      if (fs == 1) SF3R_LAUNCH(1) else if (fs == 2) SF3R_LAUNCH(2) else SF3R_LAUNCH(0)
+#undef SF3R_LAUNCH
       Pl->last_sf3_variant = 0;
+      Pl->last_sf3_static = fs;
     } else {
       const SF3Smem lay(sp.l.npairs, mapped ? 1 : 0);
       const size_t smem = (size_t)lay.total * 8;

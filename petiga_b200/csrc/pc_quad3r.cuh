@@ -110,6 +110,105 @@ __device__ __forceinline__ void sf3r_stage_ab(const uint32_t* prog, int nops, bo
   }
 }
 
+// ---- compile-time form structures.  The two list structures that matter -- first-order forms with a diagonal coefficient tensor
+//      on identity geometry (Poisson, Laplace: pairs G0G0, G1G1, G2G2) and on mapped geometry (all nine gradient pairs) -- are written
+//      down as constants, in the order build_sf_lists (pc_quad2.cu) produces them; the launcher compares the run-time lists with them
+//      and picks the specialised kernel only on an exact match (anything else runs the generic program from shared memory).  With the
+//      structure known, a warp's stage A + B program is straight-line code: no flags to test, immediate offsets, loads hoisted by the
+//      compiler (the interpreted program cost ~97 warp instructions per operation, a quarter of the kernel's instructions on identity
+//      and ~40 % on mapped geometry, profiles/r2_ncu_sf3r_v5_mesh64.json). ----
+struct SF3RStruct { int ng2, ng1, npairs; int g2_first[5], g2_oo2[4], g1_first[17], g1_oo1[16], pair_oo0[16]; };
+constexpr SF3RStruct k3rStructDiag = {2, 3, 3, {0, 2, 3, 0, 0}, {0, 4, 0, 0}, {0, 1, 2, 3}, {0, 4, 0}, {4, 0, 0}};
+constexpr SF3RStruct k3rStructFull = {4, 9, 9, {0, 4, 6, 8, 9}, {0, 1, 3, 4}, {0, 1, 2, 3, 4, 5, 6, 7, 8, 9}, {0, 1, 3, 4, 0, 3, 0, 1, 0}, {4, 3, 1, 0, 3, 0, 1, 0, 0}};
+struct SF3RProg { uint32_t op[8][8]; int n[8]; };
+constexpr SF3RProg sf3r_make_prog(const SF3RStruct& L) {      // the same longest-first deal as the run-time builder in the kernel
+  SF3RProg P = {};
+  bool done[16] = {};
+  const int ncmb = L.ng2 * 4;
+  for (int k = 0; k < ncmb; k++) {
+    int best = -1, bestn = -1;
+    for (int cmb = 0; cmb < ncmb; cmb++) {
+      if (done[cmb]) continue;
+      const int g2 = cmb >> 2;
+      const int nop = L.g1_first[L.g2_first[g2 + 1]] - L.g1_first[L.g2_first[g2]];
+      if (nop > bestn) { bestn = nop; best = cmb; }
+    }
+    done[best] = true;
+    int wmin = 0;
+    for (int w = 1; w < 8; w++) if (P.n[w] < P.n[wmin]) wmin = w;
+    const int g2 = best >> 2, q2 = best & 3;
+    bool firstc = true;
+    for (int g1 = L.g2_first[g2]; g1 < L.g2_first[g2 + 1]; g1++)
+      for (int pr = L.g1_first[g1]; pr < L.g1_first[g1 + 1]; pr++) {
+        const bool f1 = pr == L.g1_first[g1], l1 = pr + 1 == L.g1_first[g1 + 1], lc = l1 && g1 + 1 == L.g2_first[g2 + 1];
+        P.op[wmin][P.n[wmin]++] = (uint32_t)L.pair_oo0[pr] | ((uint32_t)pr << 4) | ((uint32_t)L.g1_oo1[g1] << 8) | ((uint32_t)q2 << 12) | ((uint32_t)g2 << 14) |
+                                  ((uint32_t)f1 << 16) | ((uint32_t)l1 << 17) | ((uint32_t)firstc << 18) | ((uint32_t)lc << 19);
+        firstc = false;
+      }
+  }
+  return P;
+}
+template <int FS> struct SF3RProgOf;
+template <> struct SF3RProgOf<1> { static constexpr SF3RProg P = sf3r_make_prog(k3rStructDiag); static constexpr bool mapped = false; };
+template <> struct SF3RProgOf<2> { static constexpr SF3RProg P = sf3r_make_prog(k3rStructFull); static constexpr bool mapped = true; };
+
+template <uint32_t OP, bool MAPPED>
+__device__ __forceinline__ void sf3r_op(double (&cA)[2][2], double (&cB)[2][2][2], const double* P0, const double* D, const double* PP1, const double* ccS,
+                                        double* U2, int lane, int r, int c, int dfrag, double w0q, const double (&wq12)[2]) {
+  constexpr int oo0 = OP & 15, pr = (OP >> 4) & 15, oo1 = (OP >> 8) & 15, q2 = (OP >> 12) & 3, b = q2 >> 1, x = q2 & 1;
+  constexpr bool f1 = (OP >> 16) & 1, l1 = (OP >> 17) & 1, fc = (OP >> 18) & 1, lc = (OP >> 19) & 1;
+  const double* pa = P0 + oo0 * 64 + lane;
+  const double bf = MAPPED ? D[pr * 64 + dfrag + 32 * b] : ccS[pr] * (w0q * wq12[b]);
+  if (fc) {
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) cB[mt][nt][0] = cB[mt][nt][1] = 0.0;
+  }
+  if (f1) { cA[0][0] = cA[0][1] = cA[1][0] = cA[1][1] = 0.0; }
+  dmma(cA[0][0], cA[0][1], pa[0], bf);
+  dmma(cA[1][0], cA[1][1], pa[32], bf);
+  if (l1) {
+    const double* pb = PP1 + oo1 * 64 + lane;
+    const double b0 = pb[0], b1 = pb[32];
+    dmma(cB[0][0][0], cB[0][0][1], cA[0][x], b0);
+    dmma(cB[0][1][0], cB[0][1][1], cA[0][x], b1);
+    dmma(cB[1][0][0], cB[1][0][1], cA[1][x], b0);
+    dmma(cB[1][1][0], cB[1][1][1], cA[1][x], b1);
+  }
+  if (lc) {
+    double* u = U2 + ((OP >> 12) & 15) * k3U2Q + r * 24 + 2 * c;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+        *reinterpret_cast<double2*>(u + mt * 8 * 24 + nt * 8) = make_double2(cB[mt][nt][0], cB[mt][nt][1]);
+  }
+}
+template <int FS, int W, int I>
+__device__ __forceinline__ void sf3r_ops_from(double (&cA)[2][2], double (&cB)[2][2][2], const double* P0, const double* D, const double* PP1, const double* ccS,
+                                              double* U2, int lane, int r, int c, int dfrag, double w0q, const double (&wq12)[2]) {
+  if constexpr (I < SF3RProgOf<FS>::P.n[W]) {
+    sf3r_op<SF3RProgOf<FS>::P.op[W][I], SF3RProgOf<FS>::mapped>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12);
+    sf3r_ops_from<FS, W, I + 1>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12);
+  }
+}
+template <int FS>
+__device__ __forceinline__ void sf3r_stage_ab_static(int warp, const double* P0, const double* D, const double* PP1, const double* ccS, double* U2,
+                                                     int lane, int r, int c, int dfrag, double w0q, const double (&wq12)[2]) {
+  double cA[2][2] = {{0, 0}, {0, 0}}, cB[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  switch (warp) {   // warp-uniform: each warp runs its own straight-line program
+    case 0: sf3r_ops_from<FS, 0, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 1: sf3r_ops_from<FS, 1, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 2: sf3r_ops_from<FS, 2, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 3: sf3r_ops_from<FS, 3, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 4: sf3r_ops_from<FS, 4, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 5: sf3r_ops_from<FS, 5, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    case 6: sf3r_ops_from<FS, 6, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+    default: sf3r_ops_from<FS, 7, 0>(cA, cB, P0, D, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12); break;
+  }
+}
+
 // stage C of one element for the warp (rs, par) at local row a0: its two (a0, b0) combinations, b0 = B0 and B0 + 2 with
 // B0 = (par + a0 + 1) & 1, accumulate onto the keys K0 and K0 + 1 of the running row, K0 = (B0 - a0 + 3) >> 1.
 // acc[k][nt][mt][reg]: entry (ab2 = r + 8 mt, ab1 = 2 c + reg + 8 nt) at column offset c0 = 2 k + par.  Only the key index has to be a
@@ -205,6 +304,7 @@ __device__ __forceinline__ void sf3r_stage_row(double* stg, double (&acc)[4][2][
       for (int mt = 0; mt < 2; mt++) acc[k][nt][mt][0] = acc[k][nt][mt][1] = 0.0;
 }
 
+template <int FS>      // 0: the form's lists interpreted at run time; 1 / 2: k3rStructDiag / k3rStructFull compiled in
 __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_constant__ SF3Params sp) {
   const KParams& prm = sp.k;
   const SFLists& ls = sp.l;
@@ -459,7 +559,8 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
       const double* P0 = Ring + (size_t)slot * lay.slot;
       mbar_wait(&full[slot], (it / k3Ring) & 1, 4);
       const double w0q = mapped ? 0.0 : wj0T[c];
-      sf3r_stage_ab(prog, nops, mapped, P0, P0 + 576, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12);
+      if constexpr (FS > 0) sf3r_stage_ab_static<FS>(warp, P0, P0 + 576, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12);
+      else sf3r_stage_ab(prog, nops, mapped, P0, P0 + 576, PP1, ccS, U2, lane, r, c, dfrag, w0q, wq12);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);
       it++;
@@ -505,7 +606,8 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
           const double* P0 = Ring + (size_t)slot * lay.slot;
           mbar_wait(&full[slot], (it / k3Ring) & 1, 6);
           const double w0q = mapped ? 0.0 : wj0T[(le + 1) * 4 + c];
-          sf3r_stage_ab(prog, nops, mapped, P0, P0 + 576, PP1, ccS, U2 + ((le + 1) & 1) * k3rU2, lane, r, c, dfrag, w0q, wq12);
+          if constexpr (FS > 0) sf3r_stage_ab_static<FS>(warp, P0, P0 + 576, PP1, ccS, U2 + ((le + 1) & 1) * k3rU2, lane, r, c, dfrag, w0q, wq12);
+          else sf3r_stage_ab(prog, nops, mapped, P0, P0 + 576, PP1, ccS, U2 + ((le + 1) & 1) * k3rU2, lane, r, c, dfrag, w0q, wq12);
           __syncwarp();
         }
         if (lane == 0) mbar_arrive(&empty[slot]);

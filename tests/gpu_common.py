@@ -41,7 +41,8 @@ def run_product(case, slot, form, params=(), U=None, V=None, shift=0.0, t=0.0, p
     elif slot == "JACOBIAN": g.ComputeJacobian(vU, A)
     elif slot == "IFUNCTION": g.ComputeIFunction(shift, vV, t, vU, B)
     elif slot == "IJACOBIAN": g.ComputeIJacobian(shift, vV, t, vU, A)
-    out = dict(path=int(g.GetStat("last_path")), impl=int(g.GetStat("last_impl")), sf3_variant=int(g.GetStat("last_sf3_variant")), g=g)
+    out = dict(path=int(g.GetStat("last_path")), impl=int(g.GetStat("last_impl")), sf3_variant=int(g.GetStat("last_sf3_variant")),
+               sf3_static=int(g.GetStat("last_sf3_static")), g=g)
     if A is not None:
         out["rowptr"], out["colidx"] = A.pattern()
         out["values"] = A.values()

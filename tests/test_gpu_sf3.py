@@ -82,3 +82,20 @@ def test_sf3_midsize_many_pencils_per_cta(variant):
     a = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=3)
     b = run_product(case, "SYSTEM", "POISSON", path="quadrature", quad_impl=0)
     assert rel_frobenius(a["values"], b["values"]) <= TOL and rel_frobenius(a["rhs"], b["rhs"]) <= TOL
+
+
+@pytest.mark.parametrize("static", [0, 1])
+def test_sf3r_compiled_in_structures(static):
+    """The register-carried kernel runs stages A + B either from a program interpreted at run time or from one of two compiled-in
+    form structures (diagonal gradient pairs on identity geometry, all nine on mapped geometry), chosen only when the run-time lists
+    match the constants exactly: both must give the oracle's matrix, and the expected one must be the one that ran."""
+    opts = {"sf3_variant": 0, "sf3_static": static}
+    res, _ = check_against_oracle(Case(3, p=3, N=(6, 4, 5), bcv=dall()), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["sf3_variant"] == 0 and res["sf3_static"] == (1 if static else 0)
+    res, _ = check_against_oracle(Case(3, p=3, N=(5, 4, 6), bcv=[(0, 0, 0, 1.0), (0, 1, 0, 1.0)]), "SYSTEM", "LAPLACE", path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["sf3_static"] == (1 if static else 0)
+    res, _ = check_against_oracle(Case(3, p=3, N=(6, 4, 5), bcv=dall(0.5), geometry=("perturbed", 0.05)), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["sf3_static"] == (2 if static else 0)
+    # a structure that is not compiled in (mass + stiffness: ConvTest) always runs the interpreted program
+    res, _ = check_against_oracle(Case(3, p=3, N=4, bcv=dall(0.0)), "SYSTEM", "CONVTEST", [1.5, 0.75], path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["sf3_static"] == 0

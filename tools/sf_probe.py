@@ -18,5 +18,5 @@ for name, geo in (("identity", None), ("mapped", ("perturbed", 0.05))):
         ms = 0.0
         for _ in range(3):
             g.ComputeSystem(A, B); ms += g.GetStat("last_kernel_ms") / 3
-        print(json.dumps({"geometry": name, "mesh": N, "scatter": "on" if sc == 0 else "skipped", "kernel_ms": ms, "impl": int(g.GetStat("last_impl"))}), flush=True)
+        print(json.dumps({"geometry": name, "mesh": N, "scatter": "on" if sc == 0 else "skipped", "kernel_ms": ms, "impl": int(g.GetStat("last_impl")), "static": int(g.GetStat("last_sf3_static"))}), flush=True)
     A.destroy(); B.destroy(); g.Destroy()
