@@ -236,7 +236,7 @@ def main():
             g.ComputeSystem(A, B)
         path_used = int(g.GetStat("last_path"))
         quad_flops = g.GetStat("last_flops")
-        quad_kernel_label = kernel_name(g, {1: "quadrature", 2: "kronecker"}.get(path_used, "?"))
+        quad_kernel_label = kernel_name(g, {1: "quadrature", 2: "kronecker"}.get(path_used, "?"), mapped=args.geometry != "identity")
         # -------- timed region: device-resident (inputs already in HBM) --------
         sampler = ClockSampler(local)
         sampler.start()
@@ -285,7 +285,7 @@ def main():
                 qk += g.GetStat("last_kernel_ms")
             e1.record(stream)
             barrier()
-            qflops, qlabel, qlaunch = g.GetStat("last_flops"), kernel_name(g, "quadrature"), (g.GetStat("launches") - ql0) / qsteps
+            qflops, qlabel, qlaunch = g.GetStat("last_flops"), kernel_name(g, "quadrature", mapped=args.geometry != "identity"), (g.GetStat("launches") - ql0) / qsteps
         qt = torch.tensor([e0.elapsed_time(e1) / qsteps, qk / qsteps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(qt, op=dist.ReduceOp.MAX)
@@ -501,7 +501,7 @@ def sweep_configs(stream, peaks):
         nvec = B.size if B is not None else 0
         path = {1: "quadrature", 2: "kronecker"}.get(int(g.GetStat("last_path")), "?")
         hybrid = path == "kronecker" and form == "L2PROJECTION"       # matrix by the separable path, load vector by a quadrature kernel
-        row = {"config": name, "workload": WORKLOADS[name], "path": path, "kernel": kernel_name(g, path) + (" + " + kernel_name(g, "quadrature") if hybrid else ""), "ms_per_call": ms, "steps": steps,
+        row = {"config": name, "workload": WORKLOADS[name], "path": path, "kernel": kernel_name(g, path, mapped=case.geometry is not None) + (" + " + kernel_name(g, "quadrature") if hybrid else ""), "ms_per_call": ms, "steps": steps,
                "launches_per_call": (g.GetStat("launches") - l0) / steps, "elements": nel, "nnz": nnz,
                "elements_per_s": nel / (ms * 1e-3), "value": (nnz / (ms * 1e-3) / 1e6) if nnz else None, "unit": "Mnnz/s"}
         bytes_alg = 8.0 * (nnz + nvec * (1 + (2 if state else 0))) + (8.0 * 3 * g.info()["nnp"][0] * g.info()["nnp"][1] * g.info()["nnp"][2] if case.geometry else 0.0)
@@ -539,12 +539,12 @@ WORKLOADS = {
 }
 
 
-def kernel_name(g, path):
+def kernel_name(g, path, mapped=False):
     if path == "kronecker":
         return "kron_rows_kernel"
     impl = int(g.GetStat("last_impl"))
-    if impl == 3:
-        return ("quad_sf3r_kernel" if int(g.GetStat("last_sf3_variant")) == 0 else "quad_sf3_kernel") + " (+ sf3_geom_kernel)"
+    if impl == 3:      # matrix kernel + the kernel that integrates the element vectors (and D' on mapped geometry)
+        return ("quad_sf3r_kernel" if int(g.GetStat("last_sf3_variant")) == 0 else "quad_sf3_kernel") + (" (+ sf3_geom_kernel)" if mapped else " (+ quad_vec3_kernel)")
     return {0: "quad_sf_kernel", 1: "quad_kernel", 2: "quad_gen_kernel", 4: "quad_vec3_kernel"}.get(impl, "?")
 
 
