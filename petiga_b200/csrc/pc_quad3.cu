@@ -80,6 +80,12 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
   std::vector<char> cpat((size_t)std::max(NA * NA, 1), 0);
   for (int k = 0; k < NA * NA; k++) { cpat[k] = C[k] != 0.0; sp.Cc[k] = C[k]; }
   for (int k = 0; k < NV; k++) sp.fconst[k] = fv[k];
+  for (int al = 0; al < NA; al++)
+    for (int be = 0; be < NA; be++) {
+      const int ca = base.mc0 + al, cb = base.mc0 + be;
+      if (ca < 4 && cb < 4) { sp.C4[ca * 4 + cb] = C[(size_t)al * NA + be]; if ((ca == 0 || cb == 0) && C[(size_t)al * NA + be] != 0.0) sp.c4_n = 1; }
+    }
+  for (int al = 0; al < NV; al++) if (base.vc0 + al < 4) sp.f4[base.vc0 + al] = fv[al];
   int rc = build_sf_lists(base, fi, mapped, false, false, false, cpat, NA > 0 ? 1 : 0, sp.l);
   if (rc) return nope("component lists");
   if (sp.l.NT > 4 || sp.l.npairs > k3MaxPairs || sp.l.ng2 > 4) return nope("too many tensor components");
@@ -135,8 +141,10 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
     }
     sp.dprime = Pl->d_sf3_dprime;
   }
+  const dim3 ggrid((unsigned)base.ax[0].ew, (unsigned)base.ax[1].ew, (unsigned)base.ax[2].ew);
+  if (base.ax[1].ew > 65535 || base.ax[2].ew > 65535) return nope("element box too large for a 3-D grid");
   if (mapped && sp.want_mat) {          // geometry pre-pass: D' for the matrix kernel (+ the element vectors on the way)
-    sf3_geom_kernel<<<base.nelem, 64, 0, Pl->stream>>>(sp);
+    sf3_geom_kernel<<<ggrid, 64, 0, Pl->stream>>>(sp);
     PC_CUDA(cudaGetLastError());
     Pl->launches++;
   } else if (sp.want_vec && NV > 0 && base.ax[1].ew <= 65535 && base.ax[2].ew <= 65535) {   // vector only: the lean vector kernel (pc_quadv.cuh)
@@ -146,7 +154,7 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
     PC_CUDA(cudaGetLastError());
     Pl->launches++;
   } else if (sp.want_vec) {
-    sf3_geom_kernel<<<base.nelem, 64, 0, Pl->stream>>>(sp);
+    sf3_geom_kernel<<<ggrid, 64, 0, Pl->stream>>>(sp);
     PC_CUDA(cudaGetLastError());
     Pl->launches++;
   }

@@ -40,6 +40,8 @@ struct SF3Params {
   double cconst[k3MaxPairs];      // identity geometry: D'[pair] / JW
   double Cc[16];                  // the form's constant coefficient tensor [NA][NA]
   double fconst[4];               // constant vector coefficient (when !per_qp)
+  double C4[16], f4[4];           // the same tensors zero-padded in the canonical physical order [N, d/dx0, d/dx1, d/dx2]
+  int c4_n;                       // C4 has entries in the N row / column
   int const_dp;
   int npencils, seglen, nseg;     // work items = npencils * nseg segments of <= seglen elements along axis 0
   int fixsys;                     // slot == SYSTEM with boundary conditions
@@ -133,68 +135,80 @@ __device__ __forceinline__ bool sf3_elem_on_bc(const KParams& prm, const int ID[
 // ------------------------------------------------------------------------------------------------------------------------
 // Geometry pre-pass: one 64-thread CTA per element, many CTAs per SM (latency tolerant).  Writes D'[element][pair][64] for the
 // matrix kernel (mapped geometry only) and assembles the element vector (K5-K7, K9 vector part, K10 for vectors).
+// Round-2 rewrite: the first version spent 6 300 warp instructions per element (as many as the matrix kernel: 21 of the 56 ms of
+// cfg 2g) on index arithmetic and on select chains over the run-time component ranges.  Now every loop has compile-time trip
+// counts with thread-constant sub-indices (64 threads = 64 nodes = 64 points), and the form's tensors arrive zero-padded in the
+// canonical physical order [N, d/dx0, d/dx1, d/dx2] (sp.C4, sp.f4), so the pull-back is plain 3x3 algebra:
+//   D'_GG = JW E C_GG E^T,  D'_NG = JW C_NG E^T,  D'_GN = JW E C_GN,  D'_NN = JW C_NN,   f'_G = JW E f_G,  f'_N = JW f_N
+// with E[d][i] = d xi_d / d x_i (petigamapinv.f90.in:28-31).  Tensor slots are [N (if present), xi0, xi1, xi2] by construction
+// (build_sf_lists), so slot s is physical index s + 1 - hn.
 // ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF3Params sp) {
   const KParams& prm = sp.k;
   const SFLists& ls = sp.l;
-  __shared__ double gB[96], wJ[12], pt[12], Xs[192], T1[384], T2[576], Ev[768], Fp[256];
+  __shared__ __align__(16) double gB[96], Xs[192], T1[384], T2[576], Ev[768], Fp[256], Dsh[16 * 64];
+  __shared__ double wJ[12], pt[12];
   const int gt = threadIdx.x;
-  const int NA = prm.mc1 - prm.mc0, NV = prm.vc1 - prm.vc0, NT = ls.NT;
+  const int NV = prm.vc1 - prm.vc0, NT = ls.NT;
   const bool mapped = prm.X != nullptr;
-  int ID[3];
-  {
-    int idx = blockIdx.x;
-#pragma unroll
-    for (int d = 0; d < 3; d++) { const int cc = idx % prm.ax[d].ew; idx /= prm.ax[d].ew; ID[d] = cc + prm.ax[d].es; }
-  }
-  for (int t = gt; t < 96; t += 64) {
-    const int d = t / 32, r = t % 32, o = r / 16, q = (r / 4) % 4, a = r % 4;
-    gB[t] = prm.ax[d].value[((size_t)(ID[d] * 4 + q) * 4 + a) * 5 + o];                 // Bt[d][o][q][a]
+  const int hn = ls.tN >= 0 ? 1 : 0;
+  const int ID[3] = {(int)blockIdx.x + prm.ax[0].es, (int)blockIdx.y + prm.ax[1].es, (int)blockIdx.z + prm.ax[2].es};
+  const size_t elin = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+  {  // Bt[d][o][q][a]: 96 values, thread gt loads entries gt and gt + 64 (d = 0/1 and d = 2)
+    const int r = gt & 31, o = r >> 4, q = (r >> 2) & 3, a = r & 3, d0 = gt >> 5;
+    gB[gt] = prm.ax[d0].value[((size_t)(ID[d0] * 4 + q) * 4 + a) * 5 + o];
+    if (gt < 32) gB[64 + gt] = prm.ax[2].value[((size_t)(ID[2] * 4 + q) * 4 + a) * 5 + o];
   }
   if (gt < 12) {
-    const int d = gt / 4, q = gt % 4;
+    const int d = gt >> 2, q = gt & 3;
     wJ[gt] = prm.ax[d].weight[ID[d] * 4 + q] * prm.ax[d].detJac[ID[d]];
     pt[gt] = prm.ax[d].point[ID[d] * 4 + q];
   }
   const int a = gt, ai[3] = {a & 3, (a >> 2) & 3, a >> 4};
-  int gidx = 0;
-  {
-    int mul = 1;
-#pragma unroll
-    for (int d = 0; d < 3; d++) { gidx += (prm.ax[d].offset[ID[d]] + ai[d] - prm.ax[d].gs) * mul; mul *= prm.ax[d].gw; }
-  }
+  const int gidx = (prm.ax[0].offset[ID[0]] + ai[0] - prm.ax[0].gs) +
+                   prm.ax[0].gw * ((prm.ax[1].offset[ID[1]] + ai[1] - prm.ax[1].gs) + prm.ax[1].gw * (prm.ax[2].offset[ID[2]] + ai[2] - prm.ax[2].gs));
   if (mapped) {
 #pragma unroll
     for (int i = 0; i < 3; i++) Xs[i * 64 + a] = prm.X[(size_t)gidx * 3 + i];
   }
   __syncthreads();
+  const int q0 = gt & 3, q1 = (gt >> 2) & 3, q2 = gt >> 4;       // this thread's quadrature point (and, as a0 a1 a2, its node)
   if (mapped) {   // X1 = dX/du and X0 at the points by sum factorisation (petigamapgeo.f90.in:28-43)
-    for (int t = gt; t < 384; t += 64) {              // T1[i][o0][q0][a12]
-      const int i = t / 128, r = t % 128, o0 = r / 64, q0 = (r / 16) % 4, a12 = r % 16;
-      const double* b = gB + o0 * 16 + q0 * 4;
-      const double* x = Xs + i * 64 + a12 * 4;
-      T1[t] = b[0] * x[0] + b[1] * x[1] + b[2] * x[2] + b[3] * x[3];
+    {  // T1[i][o0][q0'][a12]:  t = gt + 64 m  ->  i = m >> 1, o0 = m & 1, q0' = gt >> 4, a12 = gt & 15
+      const int qq = gt >> 4, a12 = gt & 15;
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const double* b = gB + (m & 1) * 16 + qq * 4;
+        const double* x = Xs + (m >> 1) * 64 + a12 * 4;
+        T1[gt + 64 * m] = b[0] * x[0] + b[1] * x[1] + b[2] * x[2] + b[3] * x[3];
+      }
     }
     __syncthreads();
-    for (int t = gt; t < 576; t += 64) {              // T2[i][oc][q0][q1][a2], oc: 0 = (1,0), 1 = (0,1), 2 = (0,0)
-      const int i = t / 192, r = t % 192, oc = r / 64, q0 = (r / 16) % 4, q1 = (r / 4) % 4, a2 = r % 4;
-      const int o0 = (oc == 0), o1 = (oc == 1);
-      const double* b = gB + 32 + o1 * 16 + q1 * 4;
-      const double* s = T1 + i * 128 + o0 * 64 + q0 * 16 + a2 * 4;
-      T2[t] = b[0] * s[0] + b[1] * s[1] + b[2] * s[2] + b[3] * s[3];
+    {  // T2[i][oc][q0'][q1'][a2]:  t = gt + 64 m  ->  i = m / 3, oc = m % 3 (0 = (1,0), 1 = (0,1), 2 = (0,0)), (q0', q1', a2) from gt
+      const int qa = gt >> 4, qb = (gt >> 2) & 3, a2 = gt & 3;
+#pragma unroll
+      for (int m = 0; m < 9; m++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int i = m / 3, oc = m % 3, o0 = (oc == 0), o1 = (oc == 1);
+        const double* b = gB + 32 + o1 * 16 + qb * 4;
+        const double* sx = T1 + i * 128 + o0 * 64 + qa * 16 + a2 * 4;
+        T2[gt + 64 * m] = b[0] * sx[0] + b[1] * sx[1] + b[2] * sx[2] + b[3] * sx[3];
+      }
     }
     __syncthreads();
-    for (int t = gt; t < 768; t += 64) {              // Ev[i][d][q], d = 3: the point itself
-      const int i = t / 256, r = t % 256, d = r / 64, q = r % 64, q0 = q & 3, q1 = (q >> 2) & 3, q2 = q >> 4;
-      const int oc = (d == 0) ? 0 : (d == 1 ? 1 : 2), o2 = (d == 2);
-      const double* b = gB + 64 + o2 * 16 + q2 * 4;
-      const double* s = T2 + i * 192 + oc * 64 + q0 * 16 + q1 * 4;
-      Ev[t] = b[0] * s[0] + b[1] * s[1] + b[2] * s[2] + b[3] * s[3];
+    {  // Ev[i][d][q]:  t = gt + 64 m  ->  i = m >> 2, d = m & 3 (3: the point itself), q = gt
+#pragma unroll
+      for (int m = 0; m < 12; m++) {
+        const int i = m >> 2, d = m & 3, oc = (d == 0) ? 0 : (d == 1 ? 1 : 2), o2 = (d == 2);
+        const double* b = gB + 64 + o2 * 16 + q2 * 4;
+        const double* sx = T2 + i * 192 + oc * 64 + q0 * 16 + q1 * 4;
+        Ev[gt + 64 * m] = b[0] * sx[0] + b[1] * sx[1] + b[2] * sx[2] + b[3] * sx[3];
+      }
     }
-    __syncthreads();
+    // (each thread reads back only what it wrote: Ev[.][.][gt]; no barrier)
   }
   {  // one thread per quadrature point: inverse map (petigamapinv.f90.in:28-31), weights, D', vector coefficient
-    const int q = gt, q0 = q & 3, q1 = (q >> 2) & 3, q2 = q >> 4;
+    const int q = gt;
     double E[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, x[3] = {pt[q0], pt[4 + q1], pt[8 + q2]};
     double jw = wJ[q0] * wJ[4 + q1] * wJ[8 + q2];                // W = iW jW kW, J = iJ jJ kJ (petiga3d.F90:22-28)
     if (mapped) {
@@ -212,78 +226,49 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
       E[2][0] = (a10 * a21 - a11 * a20) / det; E[2][1] = -(a00 * a21 - a01 * a20) / det; E[2][2] = (a00 * a11 - a01 * a10) / det;
       jw *= det;                                                 // detJac *= detX (petigaelem.c:1024-1029)
     }
-    // A[c][s]: physical component c of a shape function = sum_s A[c][s] * (parametric tensor component s);  A[0][tN] = 1,
-    // A[1+i][tG_d] = E[d][i].  Built once per point as a zero-padded 4x4 (compile-time indices: registers).
-    double Am[4][4];
+    if (sp.want_mat && sp.dprime) {
+      // D'4 in physical-slot order [N, xi0, xi1, xi2] into this thread's column of Dsh, then the form's pairs out of it
+      double Bm[3][3];                                           // B[i][d'] = sum_j C_GG[i][j] E[d'][j]
 #pragma unroll
-    for (int cph = 0; cph < 4; cph++)
+      for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        double v = 0.0;
-        if (cph == 0) v = (s == ls.tN) ? 1.0 : 0.0;
-        else {
+        for (int dp = 0; dp < 3; dp++) Bm[i][dp] = sp.C4[(1 + i) * 4 + 1] * E[dp][0] + sp.C4[(1 + i) * 4 + 2] * E[dp][1] + sp.C4[(1 + i) * 4 + 3] * E[dp][2];
 #pragma unroll
-          for (int d = 0; d < 3; d++) if (s == ls.tG[d]) v = E[d][cph - 1];
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int dp = 0; dp < 3; dp++) Dsh[((1 + d) * 4 + 1 + dp) * 64 + q] = jw * (E[d][0] * Bm[0][dp] + E[d][1] * Bm[1][dp] + E[d][2] * Bm[2][dp]);
+      if (sp.c4_n) {                                             // the form couples N (mass / reaction terms)
+        Dsh[q] = jw * sp.C4[0];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          Dsh[(1 + d) * 64 + q] = jw * (sp.C4[1] * E[d][0] + sp.C4[2] * E[d][1] + sp.C4[3] * E[d][2]);                  // D'[N][xi_d]
+          Dsh[((1 + d) * 4) * 64 + q] = jw * (E[d][0] * sp.C4[4] + E[d][1] * sp.C4[8] + E[d][2] * sp.C4[12]);           // D'[xi_d][N]
         }
-        Am[cph][s] = v;
       }
-    if (sp.want_mat && sp.dprime) {   // D'[s][t] = JW sum_{al,be} A[mc0+al][s] C[al][be] A[mc0+be][t]
-      double CA[4][4], Dm[16];
-#pragma unroll
-      for (int al = 0; al < 4; al++)
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int be = 0; be < 4; be++) {
-            const int cb = prm.mc0 + be;
-            double at = 0.0;
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) if (cc == cb) at = Am[cc][t];
-            if (al < NA && be < NA) acc = fma(sp.Cc[al * NA + be], at, acc);
-          }
-          CA[al][t] = acc;
-        }
-#pragma unroll
-      for (int s = 0; s < 4; s++)
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int al = 0; al < 4; al++) {
-            const int ca = prm.mc0 + al;
-            double as = 0.0;
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) if (cc == ca) as = Am[cc][s];
-            if (al < NA) acc = fma(as, CA[al][t], acc);
-          }
-          Dm[s * 4 + t] = acc * jw;
-        }
-      double* D = sp.dprime + (size_t)blockIdx.x * ls.npairs * 64 + d3_index(q0, q1, q2);
-      for (int pr = 0; pr < ls.npairs; pr++) D[(size_t)pr * 64] = Dm[ls.pair_s[pr] * 4 + ls.pair_t[pr]];
+      double* D = sp.dprime + elin * ls.npairs * 64 + d3_index(q0, q1, q2);
+      const int sh = 1 - hn;
+      for (int pr = 0; pr < ls.npairs; pr++) D[(size_t)pr * 64] = Dsh[((ls.pair_s[pr] + sh) * 4 + ls.pair_t[pr] + sh) * 64 + q];
     }
     if (sp.want_vec && NV > 0) {
-      double fv[4] = {sp.fconst[0], sp.fconst[1], sp.fconst[2], sp.fconst[3]};
+      double f4[4] = {sp.f4[0], sp.f4[1], sp.f4[2], sp.f4[3]};
       if (prm.per_qp) {
         QPoint qp;
         qp.atboundary = 0;
         qp.x[0] = x[0]; qp.x[1] = x[1]; qp.x[2] = x[2];
-        fv[0] = fv[1] = fv[2] = fv[3] = 0.0;
+        double fv[4] = {0.0, 0.0, 0.0, 0.0};
         form_coefficients<3, 1>(prm.form, prm.slot, prm.prm, prm.shift, prm.t, qp, 0, NV, nullptr, fv);
-      }
 #pragma unroll
-      for (int s = 0; s < 4; s++) {       // f'[s][q] = JW sum_al A[vc0+al][s] f[al]
-        double acc = 0.0;
+        for (int ca = 0; ca < 4; ca++) {
+          f4[ca] = 0.0;
 #pragma unroll
-        for (int al = 0; al < 4; al++) {
-          const int ca = prm.vc0 + al;
-          double as = 0.0;
-#pragma unroll
-          for (int cc = 0; cc < 4; cc++) if (cc == ca) as = Am[cc][s];
-          if (al < NV) acc = fma(as, fv[al], acc);
+          for (int al = 0; al < 4; al++) if (al < NV && prm.vc0 + al == ca) f4[ca] = fv[al];
         }
-        if (s < NT) Fp[s * 64 + q] = acc * jw;
       }
+      // f'[slot][q]: N slot (if present) first, then the three parametric gradients
+      if (hn) Fp[q] = jw * f4[0];
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+        if (hn + d < NT) Fp[(hn + d) * 64 + q] = jw * (E[d][0] * f4[1] + E[d][1] * f4[2] + E[d][2] * f4[3]);
     }
   }
   if (!sp.want_vec) return;
@@ -293,26 +278,29 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
     __syncthreads();
     double* R1 = T1;                                           // [s][q2][q1][a0]
     double* R2 = T2;                                           // [s][q2][a1][a0]
-    for (int t = gt; t < NT * 64; t += 64) {
-      const int s = t >> 6, r = t & 63, q12 = r >> 2, a0 = r & 3, o = ls.torder[s][0];
-      const double* f = Fp + s * 64 + q12 * 4;
-      const double* b = gB + o * 16 + a0;
-      R1[t] = b[0] * f[0] + b[4] * f[1] + b[8] * f[2] + b[12] * f[3];
+    {
+      const int q12 = gt >> 2, a0 = gt & 3;                    // t = gt + 64 s
+      for (int sl = 0; sl < NT; sl++) {
+        const double* f = Fp + sl * 64 + q12 * 4;
+        const double* b = gB + ls.torder[sl][0] * 16 + a0;
+        R1[gt + 64 * sl] = b[0] * f[0] + b[4] * f[1] + b[8] * f[2] + b[12] * f[3];
+      }
     }
     __syncthreads();
-    for (int t = gt; t < NT * 64; t += 64) {
-      const int s = t >> 6, r = t & 63, q2 = r >> 4, a1 = (r >> 2) & 3, a0 = r & 3, o = ls.torder[s][1];
-      const double* b = gB + 32 + o * 16 + a1;
-      const double* x = R1 + s * 64 + q2 * 16 + a0;
-      R2[t] = b[0] * x[0] + b[4] * x[4] + b[8] * x[8] + b[12] * x[12];
+    {
+      const int qq2 = gt >> 4, a1 = (gt >> 2) & 3, a0 = gt & 3;
+      for (int sl = 0; sl < NT; sl++) {
+        const double* b = gB + 32 + ls.torder[sl][1] * 16 + a1;
+        const double* xx = R1 + sl * 64 + qq2 * 16 + a0;
+        R2[gt + 64 * sl] = b[0] * xx[0] + b[4] * xx[4] + b[8] * xx[8] + b[12] * xx[12];
+      }
     }
     __syncthreads();
     const int a2 = a >> 4, a01 = a & 15;
-    for (int s = 0; s < NT; s++) {
-      const int o = ls.torder[s][2];
-      const double* b = gB + 64 + o * 16 + a2;
-      const double* x = T2 + s * 64 + a01;
-      F += b[0] * x[0] + b[4] * x[16] + b[8] * x[32] + b[12] * x[48];
+    for (int sl = 0; sl < NT; sl++) {
+      const double* b = gB + 64 + ls.torder[sl][2] * 16 + a2;
+      const double* xx = R2 + sl * 64 + a01;
+      F += b[0] * xx[0] + b[4] * xx[16] + b[8] * xx[32] + b[12] * xx[48];
     }
   }
   if (prm.slot == PETIGA_SLOT_SYSTEM && sf3_elem_on_bc(prm, ID, false)) {          // FixSystem vector part (petigaelem.c:1365-1387)
