@@ -11,6 +11,19 @@
 
 namespace pc {
 
+// tensor slots the load vector can feed: N when the form has a value term, the three gradients when it has a gradient term
+static int vector_slots(const KParams& base, const SFLists& l, const double* f4) {
+  const int NV = base.vc1 - base.vc0;
+  const bool per_qp = base.per_qp != 0;
+  const bool fN = base.vc0 == 0 && NV > 0 && (per_qp || f4[0] != 0.0);
+  bool fG = false;
+  for (int ca = 1; ca < 4; ca++) if (ca >= base.vc0 && ca < base.vc1 && (per_qp || f4[ca] != 0.0)) fG = true;
+  int m = 0;
+  if (fN && l.tN >= 0) m |= 1 << l.tN;
+  if (fG) for (int d = 0; d < 3; d++) if (l.tG[d] >= 0) m |= 1 << l.tG[d];
+  return m;
+}
+
 // vector-only assembly (pc_quadv.cuh): IGAComputeVector, or the load vector of a system whose matrix the separable path has written
 int launch_quadrature_vec3(petiga_cuda_plan* Pl, const KParams& base) {
   const int dim = base.dim, dof = base.dof;
@@ -40,6 +53,8 @@ int launch_quadrature_vec3(petiga_cuda_plan* Pl, const KParams& base) {
   if (build_sf_lists(base, fi, base.X != nullptr, false, false, false, cpat, 0, sp.l)) return nope("component lists");
   if (sp.l.NT > 4) return nope("too many tensor components");
   for (int t = 0; t < sp.l.NT; t++) for (int d = 0; d < 3; d++) if (sp.l.torder[t][d] > 1) return nope("second derivatives");
+  for (int al = 0; al < NV; al++) if (base.vc0 + al < 4) sp.f4[base.vc0 + al] = fv[al];
+  sp.vslots = vector_slots(base, sp.l, sp.f4);
   sp.want_vec = 1;
   if (base.nelem <= 0) return 0;
   const int n3 = (p + 1) * (p + 1) * (p + 1), threads = (n3 + 31) / 32 * 32;
@@ -89,7 +104,7 @@ int launch_quadrature_sf3(petiga_cuda_plan* Pl, const KParams& base) {
   int rc = build_sf_lists(base, fi, mapped, false, false, false, cpat, NA > 0 ? 1 : 0, sp.l);
   if (rc) return nope("component lists");
   if (sp.l.NT > 4 || sp.l.npairs > k3MaxPairs || sp.l.ng2 > 4) return nope("too many tensor components");
-  for (int t = 0; t < sp.l.NT; t++) for (int d = 0; d < 3; d++) if (sp.l.torder[t][d] > 1) return nope("second derivatives");
+  sp.vslots = vector_slots(base, sp.l, sp.f4);
   // per-axis pair-product tables in the fragment layout, once per plan
   for (int d = 0; d < 3; d++) {
     if (!Pl->d_sf3pp[d]) {

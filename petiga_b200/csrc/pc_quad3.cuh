@@ -42,6 +42,7 @@ struct SF3Params {
   double fconst[4];               // constant vector coefficient (when !per_qp)
   double C4[16], f4[4];           // the same tensors zero-padded in the canonical physical order [N, d/dx0, d/dx1, d/dx2]
   int c4_n;                       // C4 has entries in the N row / column
+  int vslots;                     // bit s: tensor slot s can receive a load term (geometry pre-pass: the other slots are skipped)
   int const_dp;
   int npencils, seglen, nseg;     // work items = npencils * nseg segments of <= seglen elements along axis 0
   int fixsys;                     // slot == SYSTEM with boundary conditions
@@ -221,9 +222,10 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
       }
       const double a00 = X1[0][0], a01 = X1[0][1], a02 = X1[0][2], a10 = X1[1][0], a11 = X1[1][1], a12 = X1[1][2], a20 = X1[2][0], a21 = X1[2][1], a22 = X1[2][2];
       const double det = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
-      E[0][0] = (a11 * a22 - a12 * a21) / det; E[0][1] = -(a01 * a22 - a02 * a21) / det; E[0][2] = (a01 * a12 - a02 * a11) / det;
-      E[1][0] = -(a10 * a22 - a12 * a20) / det; E[1][1] = (a00 * a22 - a02 * a20) / det; E[1][2] = -(a00 * a12 - a02 * a10) / det;
-      E[2][0] = (a10 * a21 - a11 * a20) / det; E[2][1] = -(a00 * a21 - a01 * a20) / det; E[2][2] = (a00 * a11 - a01 * a10) / det;
+      const double idet = 1.0 / det;                             // one division instead of nine (each is ~25 instructions)
+      E[0][0] = (a11 * a22 - a12 * a21) * idet; E[0][1] = -(a01 * a22 - a02 * a21) * idet; E[0][2] = (a01 * a12 - a02 * a11) * idet;
+      E[1][0] = -(a10 * a22 - a12 * a20) * idet; E[1][1] = (a00 * a22 - a02 * a20) * idet; E[1][2] = -(a00 * a12 - a02 * a10) * idet;
+      E[2][0] = (a10 * a21 - a11 * a20) * idet; E[2][1] = -(a00 * a21 - a01 * a20) * idet; E[2][2] = (a00 * a11 - a01 * a10) * idet;
       jw *= det;                                                 // detJac *= detX (petigaelem.c:1024-1029)
     }
     if (sp.want_mat && sp.dprime) {
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
     {
       const int q12 = gt >> 2, a0 = gt & 3;                    // t = gt + 64 s
       for (int sl = 0; sl < NT; sl++) {
+        if (!((sp.vslots >> sl) & 1)) continue;                  // slots the load never feeds (Poisson: only N) are skipped in all three stages
         const double* f = Fp + sl * 64 + q12 * 4;
         const double* b = gB + ls.torder[sl][0] * 16 + a0;
         R1[gt + 64 * sl] = b[0] * f[0] + b[4] * f[1] + b[8] * f[2] + b[12] * f[3];
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
     {
       const int qq2 = gt >> 4, a1 = (gt >> 2) & 3, a0 = gt & 3;
       for (int sl = 0; sl < NT; sl++) {
+        if (!((sp.vslots >> sl) & 1)) continue;
         const double* b = gB + 32 + ls.torder[sl][1] * 16 + a1;
         const double* xx = R1 + sl * 64 + qq2 * 16 + a0;
         R2[gt + 64 * sl] = b[0] * xx[0] + b[4] * xx[4] + b[8] * xx[8] + b[12] * xx[12];
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
     __syncthreads();
     const int a2 = a >> 4, a01 = a & 15;
     for (int sl = 0; sl < NT; sl++) {
+      if (!((sp.vslots >> sl) & 1)) continue;
       const double* b = gB + 64 + ls.torder[sl][2] * 16 + a2;
       const double* xx = R2 + sl * 64 + a01;
       F += b[0] * xx[0] + b[4] * xx[16] + b[8] * xx[32] + b[12] * xx[48];

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(((P + 1) * (P + 1) * (P + 1) + 31) / 32 * 32) 
   double* R2 = T2;                                             // [s][q2][a1][a0]
   for (int t = gt; t < NT * NNN; t += T) {
     const int s = t / NNN, r = t % NNN, q12 = r / N, a0 = r % N, o = ls.torder[s][0];
+    if (!((sp.vslots >> s) & 1)) continue;                       // tensor slots the load never feeds
     const double* f = Fp + s * NNN + q12 * N;
     const double* b = gB + o * NN + a0;
     double acc = 0.0;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(((P + 1) * (P + 1) * (P + 1) + 31) / 32 * 32) 
   __syncthreads();
   for (int t = gt; t < NT * NNN; t += T) {
     const int s = t / NNN, r = t % NNN, q2 = r / NN, a1 = (r / N) % N, a0 = r % N, o = ls.torder[s][1];
+    if (!((sp.vslots >> s) & 1)) continue;
     const double* b = gB + 2 * NN + o * NN + a1;
     const double* x = R1 + s * NNN + q2 * NN + a0;
     double acc = 0.0;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(((P + 1) * (P + 1) * (P + 1) + 31) / 32 * 32) 
   {
     const int a2 = a / NN, a01 = a % NN;
     for (int s = 0; s < NT; s++) {
+      if (!((sp.vslots >> s) & 1)) continue;
       const int o = ls.torder[s][2];
       const double* b = gB + 4 * NN + o * NN + a2;
       const double* x = R2 + s * NNN + a01;
