@@ -323,8 +323,10 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
   uint64_t* full = reinterpret_cast<uint64_t*>(sm3 + lay.bars);
   uint64_t* empty = full + k3Ring;
   uint64_t* staged = empty + k3Ring;            // [2]: a staging buffer holds a row (arrivals: the two warps of the pair)
-  volatile int* drained = reinterpret_cast<volatile int*>(staged + 2);   // [flush warp]: flush events this warp has finished reading (a counter,
-                                                                         // not an mbarrier: a lagging warp must be able to test an event several phases old)
+  uint64_t* drained = staged + 2;               // [2]: the flush warps have read it (arrivals: one per flush warp).  Only the pair that
+                                                //      stages event n waits here, for event n - 2: it is never more than one phase away from
+                                                //      the barrier, which is what a parity wait needs; everybody else meets the flush warps at
+                                                //      the end of a work item on a named barrier (bar.sync 2)
   const int tid = threadIdx.x;
   const int ew0 = prm.ax[0].ew, ew1 = prm.ax[1].ew;
   const int nwork = sp.npencils * sp.nseg;
@@ -332,8 +334,7 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
 
   if (tid == 0) {
     for (int k = 0; k < k3Ring; k++) { mbar_init(&full[k], 1); mbar_init(&empty[k], k3AsmThreads / 32); }
-    for (int k = 0; k < 2; k++) mbar_init(&staged[k], 2);
-    for (int k = 0; k < k3rFlushWarps; k++) drained[k] = 0;
+    for (int k = 0; k < 2; k++) { mbar_init(&staged[k], 2); mbar_init(&drained[k], k3rFlushWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < k3MaxPairs) ccS[tid] = sp.cconst[tid];
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
             for (int k = 0; k < 4; k++) vv[j][k] = stg[(fw * NJ + j) * k3SA + lane + 32 * k];
           }
           __syncwarp();
-          if (lane == 0) { __threadfence_block(); drained[fw] = (int)(n + 1); }   // the row is in registers: the buffer may be refilled
+          if (lane == 0) mbar_arrive(&drained[b]);                   // the row is in registers: the buffer may be refilled
           if (!prm.noscatter) {
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
@@ -434,9 +435,10 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
             }
           }
           __syncwarp();
-          if (lane == 0) { __threadfence_block(); drained[fw] = (int)(n + 1); }
+          if (lane == 0) mbar_arrive(&drained[b]);
         }
       }
+      asm volatile("bar.sync 2, %0;" ::"n"(k3AsmThreads + 32 * k3rFlushWarps) : "memory");   // the work item's rows are out: its tables may be rewritten
     }
     return;
   }
@@ -478,11 +480,6 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
     for (int nt = 0; nt < 2; nt++)
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) acc[k][nt][mt][0] = acc[k][nt][mt][1] = 0.0;
-  auto wait_drained = [&](uint32_t nev) {   // until the flush warps have finished reading the first nev flush events
-    for (int k = 0; k < k3rFlushWarps; k++)
-      while ((uint32_t)drained[k] < nev) __nanosleep(64);            // (a spinning pair takes issue slots from the six working warps)
-    __threadfence_block();
-  };
   uint32_t it = 0;       // ring position of the next element whose stages A + B have not run yet
   uint32_t nflush = 0;   // flush events before the current work item
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -493,8 +490,6 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
     const int off_first = prm.ax[0].offset[prm.ax[0].es + le0];
     const int Gf = off_first - prm.ax[0].gs;
     const int nrows = nel + 3;
-    // the flush warps read the row tables of the previous work item until its last rows are drained
-    wait_drained(nflush);
     bar_asm();
     {
       const double* g1p = sp.pp[1] + (size_t)e1 * 576;
@@ -593,7 +588,7 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
       if (a0 == 0) {   // row le is complete: stage it for the flush warps (event nflush + le)
         const uint32_t n = nflush + le;
         const int b = n & 1;
-        if (n >= 2) wait_drained(n - 1);                                   // the buffer's previous row (event n - 2) has been read
+        if (n >= 2) mbar_wait(&drained[b], ((n >> 1) & 1) ^ 1, 5);        // the buffer's previous row (event n - 2) has been read
         double* stg = Stage + b * k3rStage;
         if (par == 0) sf3r_stage_row<0>(stg, acc, r, c); else sf3r_stage_row<1>(stg, acc, r, c);
         __syncwarp();
@@ -620,14 +615,17 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
       if ((row & 3) == rs) {
         const uint32_t n = nflush + row;
         const int b = n & 1;
-        if (n >= 2) wait_drained(n - 1);
+        if (n >= 2) mbar_wait(&drained[b], ((n >> 1) & 1) ^ 1, 7);
         double* stg = Stage + b * k3rStage;
         if (par == 0) sf3r_stage_row<0>(stg, acc, r, c); else sf3r_stage_row<1>(stg, acc, r, c);
         __syncwarp();
         if (lane == 0) mbar_arrive(&staged[b]);
       }
+      bar_asm();   // the three tail rows are staged in event order: the parity wait above is only valid one phase away from the barrier
     }
     nflush += nel + 3;
+    // the flush warps read this work item's row tables until its last rows are out
+    asm volatile("bar.sync 2, %0;" ::"n"(k3AsmThreads + 32 * k3rFlushWarps) : "memory");
   }
 }
 
