@@ -99,3 +99,14 @@ def test_sf3r_compiled_in_structures(static):
     # a structure that is not compiled in (mass + stiffness: ConvTest) always runs the interpreted program
     res, _ = check_against_oracle(Case(3, p=3, N=4, bcv=dall(0.0)), "SYSTEM", "CONVTEST", [1.5, 0.75], path="quadrature", quad_impl=3, tol=TOL, options=opts)
     assert res["sf3_static"] == 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_sf3_long_pencils_are_segmented(variant):
+    """Pencils longer than the row tables of a work item (157 elements) are cut into segments; the rows shared by two segments
+    receive their partial sums from both (tail flush of the first, head rows of the second)."""
+    opts = {"sf3_variant": variant}
+    res, _ = check_against_oracle(Case(3, p=3, N=(170, 1, 2), bcv=dall()), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["impl"] == 3 and res["sf3_variant"] == variant
+    res, _ = check_against_oracle(Case(3, p=3, N=(330, 1, 1), bcv=dall(0.5), geometry=("perturbed", 0.02)), "SYSTEM", "POISSON", path="quadrature", quad_impl=3, tol=TOL, options=opts)
+    assert res["impl"] == 3 and res["sf3_variant"] == variant
