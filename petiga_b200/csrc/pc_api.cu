@@ -359,6 +359,7 @@ int petiga_cuda_set_option(petiga_cuda_plan* P, const char* name, double value) 
   if (!strcmp(name, "path")) { int v = (int)value; if (v < 0 || v > 2) return PETIGA_CUDA_ERR_ARG; P->path = v; return 0; }
   if (!strcmp(name, "scatter")) { P->scatter = (int)value; return 0; }
   if (!strcmp(name, "quad_impl")) { int v = (int)value; if (v < -1 || v > 3) return PETIGA_CUDA_ERR_ARG; P->quad_impl = v; return 0; }
+  if (!strcmp(name, "kron_minb_rows")) { P->kron_minb_rows = (int)value; P->config_version++; return 0; }
   if (!strcmp(name, "kron_bulk")) { P->kron_bulk = value != 0; P->config_version++; return 0; }
   if (!strcmp(name, "sf3_static")) { P->sf3_static = value != 0; return 0; }
   if (!strcmp(name, "sf3_variant")) { int v = (int)value; if (v < 0 || v > 1) return PETIGA_CUDA_ERR_ARG; P->sf3_variant = v; return 0; }

@@ -58,6 +58,7 @@ struct KronParams {
   unsigned char combo_rs0[36], combo_ij[36], combo_first[37];
   signed char slotA[9], slotB[9];   // ... as (at most) two order-pair indices per block entry, -1 = none; two_slot = 0 when an entry has more
   int two_slot;
+  int minb_rows;          // scalar case: pencils at least this long run the 3-CTA (80-register) instantiation
   int bulk;               // dof 1 fast passes: rows staged in shared memory and written by cp.async.bulk (TMA) stores
   KronTerm terms[kMaxTerms];
   KronVTerm vterms[8];
@@ -154,8 +155,11 @@ __device__ __forceinline__ int bcode(int col, int nnp, int periodic) { return pe
 // One CTA per (A_j, A_k) pencil of owned rows; warps walk the rows A_i of the pencil; lanes walk the entries of a
 // row in storage order, so every store instruction writes 256 contiguous bytes.
 // PF > 0: all axes have degree PF, so a full-width interior row has compile-time extents and its loop unrolls completely
-template <int DOF, int PF>
-__global__ void __launch_bounds__(256, (DOF == 1) ? 4 : 2) kron_rows_kernel(const __grid_constant__ KronParams kp) {
+// MINB: resident CTAs per SM the register budget is set for.  Scalar case, measured (tools/kron_probe.py): 3 CTAs of 80 registers are
+// 3 % faster than 4 of 64 on long pencils (128^3: 0.986 vs 1.011 ms) and 5 % slower on short ones (64^3, an 8-GPU share), where the
+// latency-bound prologue and boundary rows want more warps; the launcher picks by pencil length.  dof > 1: 2 (128 registers).
+template <int DOF, int PF, int MINB>
+__global__ void __launch_bounds__(256, MINB) kron_rows_kernel(const __grid_constant__ KronParams kp) {
   extern __shared__ __align__(16) double dynstage[];   // dof > 1: kStageCap doubles per warp
   __shared__ double G[4][DOF * DOF][kMaxWW];     // G^{rs0}_{ij}[cjk] = sum_terms c * M_j^{rs1}[A_j][cj] * M_k^{rs2}[A_k][ck]
   __shared__ int jkinfo[kMaxWW];                 // code_j | code_k<<2 | diag<<4 | P2<<8 | P3<<16   (P1 in jkp1)
@@ -836,10 +840,12 @@ static int launch_kron_kernel(petiga_cuda_plan* P, const KronParams& kp) {
   if (L.dim < 3 || (L.dof != 1 && pf > 2)) pf = 0;
   size_t dyn = L.dof > 1 ? (size_t)(threads / 32) * kStageCap * sizeof(double) : 0;
   if (L.dof == 1 && kp.bulk && pf > 0) dyn = (size_t)(threads / 32) * (4 * (2 * pf + 1) * (2 * pf + 1) * (2 * pf + 1) + 4) * sizeof(double);
-#define KL(DOF_, PF_) if (L.dof == DOF_ && pf == PF_) { \
-    if (dyn) PC_CUDA(cudaFuncSetAttribute(kron_rows_kernel<DOF_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-    kron_rows_kernel<DOF_, PF_><<<blocks, threads, dyn, P->stream>>>(kp); }
-  KL(1, 0) KL(1, 1) KL(1, 2) KL(1, 3) KL(1, 4) KL(2, 0) KL(3, 0) KL(2, 1) KL(2, 2) KL(3, 1) KL(3, 2)
+  const int minb = L.dof > 1 ? 2 : (L.ax[0].lw >= kp.minb_rows ? 3 : 4);
+#define KL(DOF_, PF_, MB_) if (L.dof == DOF_ && pf == PF_ && minb == MB_) { \
+    if (dyn) PC_CUDA(cudaFuncSetAttribute(kron_rows_kernel<DOF_, PF_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    kron_rows_kernel<DOF_, PF_, MB_><<<blocks, threads, dyn, P->stream>>>(kp); }
+  KL(1, 0, 3) KL(1, 1, 3) KL(1, 2, 3) KL(1, 3, 3) KL(1, 4, 3) KL(1, 0, 4) KL(1, 1, 4) KL(1, 2, 4) KL(1, 3, 4) KL(1, 4, 4)
+  KL(2, 0, 2) KL(3, 0, 2) KL(2, 1, 2) KL(2, 2, 2) KL(3, 1, 2) KL(3, 2, 2)
 #undef KL
   PC_CUDA(cudaGetLastError());
   P->launches++;
@@ -910,6 +916,7 @@ int launch_kronecker(petiga_cuda_plan* P, int slot, int block, double* values, d
   kp.rowbase = P->d_rowbase; kp.localrow = P->d_localrow; kp.fixtable = P->d_fixtable;
   kp.dim = L.dim; kp.dof = L.dof; kp.block = block; kp.slot = slot; kp.simple = simple; kp.wfull0 = 2 * L.ax[0].p + 1;
   kp.bulk = P->kron_bulk;
+  kp.minb_rows = P->kron_minb_rows;
   kp.values = values; kp.rhs = rhs;
   const double* prm = P->slots[slot].prm;
 #define HT(DIM_, DOF_) if (L.dim == DIM_ && L.dof == DOF_) host_terms<DIM_, DOF_>(form, slot, prm, fi, kp);

@@ -78,6 +78,7 @@ struct petiga_cuda_plan {
   std::vector<unsigned char> kron_cache;   // cached parameter block of the separable path
   int kron_cache_slot = -1, kron_cache_block = -1;
   long kron_cache_version = -1, config_version = 0;   // bumped by form_select / set_bc / set_geometry
+  int kron_minb_rows = 100;       // separable path, dof 1: axis-0 rows per pencil from which the 3-CTA instantiation is used
   int kron_bulk = 0;              // separable path, dof 1: 1 = rows staged in shared memory and written by cp.async.bulk stores
   int sf3_variant = 0;            // third-generation kernel: 0 = register-carried rows where the axis-0 rows advance one per element, 1 = shared-memory window always
   int last_sf3_variant = 0;
