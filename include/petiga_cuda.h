@@ -151,8 +151,15 @@ int         petiga_cuda_measure_fp64(int device, double seconds, double *tflops_
 int petiga_cuda_plan_create(petiga_cuda_plan **plan, const petiga_cuda_space *space, int rank, int nranks,
                             void *nccl_comm, void *stream, int device);
 int petiga_cuda_plan_destroy(petiga_cuda_plan *plan);
-int petiga_cuda_set_option(petiga_cuda_plan *plan, const char *name, double value);   /* "path", "scatter" */
-int petiga_cuda_get_stat(petiga_cuda_plan *plan, const char *name, double *value);    /* "launches", "last_path", ... */
+/* options: "path" (0 auto, 1 quadrature, 2 separable), "quad_impl" (-1 library's choice, 0 sum-factorised, 1 pair loop, 2 generic,
+            3 third generation), "sf3_variant" (0 rows carried in the DMMA accumulators where the axis-0 rows advance one per element,
+            1 shared-memory window always), "sf3_static" (1 use the compiled-in form structures when the run-time lists match),
+            "kron_minb_rows" (scalar separable kernel: pencil length from which the 3-CTA build runs), "kron_bulk" (1: cp.async.bulk row
+            stores, measured slower), "scatter" (99: integrate but skip the global reductions, profiling only)
+   stats:   "launches", "last_path", "last_impl", "last_sf3_variant", "last_sf3_static", "last_kernel_ms", "last_flops", "num_sms",
+            "nghostrows", "nnz_loc" */
+int petiga_cuda_set_option(petiga_cuda_plan *plan, const char *name, double value);
+int petiga_cuda_get_stat(petiga_cuda_plan *plan, const char *name, double *value);
 
 /* geometry: host ghost-box arrays X[gw_k][gw_j][gw_i][nsd], W[gw_k][gw_j][gw_i] (W may be NULL);
    nsd must equal dim.  Pass X == NULL to return to the identity map. */
