@@ -144,6 +144,13 @@ __device__ __forceinline__ bool sf3_elem_on_bc(const KParams& prm, const int ID[
 // with E[d][i] = d xi_d / d x_i (petigamapinv.f90.in:28-31).  Tensor slots are [N (if present), xi0, xi1, xi2] by construction
 // (build_sf_lists), so slot s is physical index s + 1 - hn.
 // ------------------------------------------------------------------------------------------------------------------------
+// 4-term dot product of two 32-byte aligned shared-memory quadruples (two LDS.128 each instead of four LDS.64)
+__device__ __forceinline__ double dot4_aligned(const double* b, const double* x) {
+  const double2 b0 = *reinterpret_cast<const double2*>(b), b1 = *reinterpret_cast<const double2*>(b + 2);
+  const double2 x0 = *reinterpret_cast<const double2*>(x), x1 = *reinterpret_cast<const double2*>(x + 2);
+  return b0.x * x0.x + b0.y * x0.y + b1.x * x1.x + b1.y * x1.y;
+}
+
 __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF3Params sp) {
   const KParams& prm = sp.k;
   const SFLists& ls = sp.l;
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
       for (int m = 0; m < 6; m++) {
         const double* b = gB + (m & 1) * 16 + qq * 4;
         const double* x = Xs + (m >> 1) * 64 + a12 * 4;
-        T1[gt + 64 * m] = b[0] * x[0] + b[1] * x[1] + b[2] * x[2] + b[3] * x[3];
+        T1[gt + 64 * m] = dot4_aligned(b, x);
       }
     }
     __syncthreads();
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
         const int i = m / 3, oc = m % 3, o0 = (oc == 0), o1 = (oc == 1);
         const double* b = gB + 32 + o1 * 16 + qb * 4;
         const double* sx = T1 + i * 128 + o0 * 64 + qa * 16 + a2 * 4;
-        T2[gt + 64 * m] = b[0] * sx[0] + b[1] * sx[1] + b[2] * sx[2] + b[3] * sx[3];
+        T2[gt + 64 * m] = dot4_aligned(b, sx);
       }
     }
     __syncthreads();
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(64) sf3_geom_kernel(const __grid_constant__ SF
         const int i = m >> 2, d = m & 3, oc = (d == 0) ? 0 : (d == 1 ? 1 : 2), o2 = (d == 2);
         const double* b = gB + 64 + o2 * 16 + q2 * 4;
         const double* sx = T2 + i * 192 + oc * 64 + q0 * 16 + q1 * 4;
-        Ev[gt + 64 * m] = b[0] * sx[0] + b[1] * sx[1] + b[2] * sx[2] + b[3] * sx[3];
+        Ev[gt + 64 * m] = dot4_aligned(b, sx);
       }
     }
     // (each thread reads back only what it wrote: Ev[.][.][gt]; no barrier)
