@@ -94,7 +94,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void bar_asm() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // Dirichlet value / Neumann load of local node (a0,a1,a2) of element ID (dof = 1): BuildFix / AddFixa / AddFlux, petigaelem.c:1166-1283
