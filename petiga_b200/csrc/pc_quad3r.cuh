@@ -213,10 +213,23 @@ __device__ __forceinline__ void sf3r_stage_ab_static(int warp, const double* P0,
 // B0 = (par + a0 + 1) & 1, accumulate onto the keys K0 and K0 + 1 of the running row, K0 = (B0 - a0 + 3) >> 1.
 // acc[k][nt][mt][reg]: entry (ab2 = r + 8 mt, ab1 = 2 c + reg + 8 nt) at column offset c0 = 2 k + par.  Only the key index has to be a
 // compile-time constant (registers); everything else is an address.
-template <int K0>
+// FS > 0: the number of g2 groups and their order pairs are compile-time constants (all loads of the loop can be issued up front);
+// the values are those of k3rStructDiag / k3rStructFull (checked at compile time below)
+__host__ __device__ constexpr int sf3r_ng2(int fs) { return fs == 1 ? 2 : 4; }
+__host__ __device__ constexpr int sf3r_g2_oo2(int fs, int g2) { return fs == 1 ? (g2 == 0 ? 0 : 4) : (g2 == 0 ? 0 : g2 == 1 ? 1 : g2 == 2 ? 3 : 4); }
+static_assert(sf3r_ng2(1) == k3rStructDiag.ng2 && sf3r_ng2(2) == k3rStructFull.ng2, "structure constants");
+static_assert(sf3r_g2_oo2(1, 0) == k3rStructDiag.g2_oo2[0] && sf3r_g2_oo2(1, 1) == k3rStructDiag.g2_oo2[1], "structure constants");
+static_assert(sf3r_g2_oo2(2, 0) == k3rStructFull.g2_oo2[0] && sf3r_g2_oo2(2, 1) == k3rStructFull.g2_oo2[1] &&
+              sf3r_g2_oo2(2, 2) == k3rStructFull.g2_oo2[2] && sf3r_g2_oo2(2, 3) == k3rStructFull.g2_oo2[3], "structure constants");
+template <int K0, int FS>
 __device__ __forceinline__ void sf3r_stage_c(const SFLists& ls, const double* PP2, const double* ub0, double (&acc)[4][2][2][2], int lane) {
-  for (int g2 = 0; g2 < ls.ng2; g2++) {
-    const double* pa = PP2 + ls.g2_oo2[g2] * 64 + lane;
+  constexpr int NG2 = FS > 0 ? sf3r_ng2(FS) : 0;
+  const int ng2 = FS > 0 ? NG2 : ls.ng2;
+#pragma unroll
+  for (int g2 = 0; g2 < (FS > 0 ? NG2 : 4); g2++) {
+    if (g2 >= ng2) break;
+    const int oo2 = FS > 0 ? sf3r_g2_oo2(FS, g2) : ls.g2_oo2[g2];
+    const double* pa = PP2 + oo2 * 64 + lane;
     const double a0f = pa[0], a1f = pa[32];
     const double* ub = ub0 + g2 * 4 * k3U2Q;
 #pragma unroll
@@ -574,9 +587,9 @@ __global__ void __launch_bounds__(k3rThreads, 1) quad_sf3r_kernel(const __grid_c
         const int b00 = (par + a0 + 1) & 1, K0 = (b00 - a0 + 3) >> 1;
         const double* ub0 = U2c + c * k3U2Q + (a0 * 4 + b00) * 24 + r;
         if (!efix) {
-          if (K0 == 0) sf3r_stage_c<0>(ls, PP2, ub0, acc, lane);
-          else if (K0 == 1) sf3r_stage_c<1>(ls, PP2, ub0, acc, lane);
-          else sf3r_stage_c<2>(ls, PP2, ub0, acc, lane);
+          if (K0 == 0) sf3r_stage_c<0, FS>(ls, PP2, ub0, acc, lane);
+          else if (K0 == 1) sf3r_stage_c<1, FS>(ls, PP2, ub0, acc, lane);
+          else sf3r_stage_c<2, FS>(ls, PP2, ub0, acc, lane);
         } else {
           double T[2][2][2][2];
           sf3r_stage_c_fix(prm, ls, PP2, ub0, T, lane, a0, b00, fv, ff, ff + 64);
