@@ -27,6 +27,9 @@ def _system(case, form, prm=()):
     (Case(2, p=3, N=(12, 9), bcv=dall(2, 0.5)), "POISSON", ()),
     (Case(3, dof=3, p=2, N=5, bcv=[(0, 0, c, 0.0) for c in range(3)] + [(0, 1, 0, 1.0)]), "ELASTICITY3D", (1.0, 1.0)),
     (Case(3, dof=3, p=2, N=5, bcv=[(0, 0, c, 0.0) for c in range(3)] + [(0, 1, 0, 1.0)], mattype="aij"), "ELASTICITY3D", (1.0, 1.0)),
+    (Case(3, dof=2, p=2, N=(4, 3, 5)), "MASS", ()),                                   # BAIJ bs = 2
+    (Case(2, dof=2, p=3, N=(7, 6), periodic=(True, False), mattype="aij"), "MASS", ()),
+    (Case(1, p=3, N=17, bcv=[(0, 0, 0, 1.0), (0, 1, 0, 2.0)]), "POISSON", ()),
 ])
 def test_matmult_matches_scipy(case, form, prm):
     g, A, B = _system(case, form, prm)
@@ -75,3 +78,16 @@ def test_ksp_argument_checks():
     g, A, B = _system(case, "POISSON")
     with pytest.raises(pb.IGAError):
         g.Solve(A, B, B)                                   # b and x must differ
+
+
+def test_ksp_block_mass_system():
+    """A dof-2 mass system (BAIJ blocks of 2 x 2): the block SpMV inside CG against a direct solve."""
+    case = Case(3, dof=2, p=2, N=(5, 4, 3))
+    g, A, B = _system(case, "MASS")
+    rp, ci = A.pattern()
+    n = (len(rp) - 1) * 2
+    M = sp.bsr_matrix((A.values().reshape(-1, 2, 2), ci, rp), shape=(n, n)).tocsc()
+    xs = spla.spsolve(M, B.get())
+    X = g.CreateVec()
+    its, rel = g.Solve(A, B, X, rtol=1e-12)
+    assert rel <= 1e-12 and np.linalg.norm(X.get() - xs) <= 1e-9 * np.linalg.norm(xs)
