@@ -34,3 +34,29 @@ def test_reference_arm_under_torchrun_two_ranks():
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     check(r.stdout)
+
+
+def test_product_code_does_not_reach_into_oracle_or_tests():
+    """The oracle is test infrastructure: the product package must not import it at all, and bench.py may execute it only in the
+    cpu_baseline / reference-arm legs (function-local imports of oracle.cpu_reference), never at module level and never `tests`."""
+    import ast
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "petiga_b200", "*.py")):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] in ("oracle", "tests") for n in names), (path, names)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in tree.body:      # module level
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = node.module if isinstance(node, ast.ImportFrom) else node.names[0].name
+            assert (mod or "").split(".")[0] not in ("oracle", "tests"), mod
+    allowed = {"cpu_reference_run", "main"}       # main(): only the cfg-1 full-size CPU figure inside the cpu_baseline block
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] in ("oracle", "tests"):
+                assert node.module.startswith("oracle.cpu_reference") and fn.name in allowed, (fn.name, node.module)
